@@ -1,0 +1,103 @@
+"""ctypes binding of libgsn_b200.so (include/gsn_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call
+fails, the product path raises.  PyTorch is only used for device memory and
+streams; every tensor crosses the boundary as a raw pointer.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from .patterns import GsnPlan
+
+_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libgsn_b200.so')
+
+GSN_OK = 0
+_ERRORS = {-1: 'GSN_E_INVALID (bad argument)', -2: 'GSN_E_UNSUPPORTED (shape outside the built kernels)',
+           -3: 'GSN_E_WORKSPACE (workspace too small)', -4: 'GSN_E_CUDA'}
+
+S_GRAPH_TOO_LARGE, S_CROSS_GRAPH_EDGE, S_MISSING_EDGE, S_INDEX_RANGE = 1, 2, 4, 8
+
+_vp, _i64, _i32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_size_t
+_szp = ctypes.POINTER(ctypes.c_size_t)
+_planp = ctypes.POINTER(GsnPlan)
+
+_SIGNATURES = {
+    'gsn_abi_version': (ctypes.c_int, []),
+    'gsn_last_cuda_error': (ctypes.c_char_p, []),
+    'gsn_graph_workspace_bytes': (ctypes.c_int, [_i64, _i64, _i32, _szp]),
+    'gsn_graph_build': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _sz, _vp, _vp]),
+    'gsn_count_scratch_bytes': (ctypes.c_int, [_i64, _i64, _planp, _szp]),
+    'gsn_count_pattern': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _planp, _vp, _i64, _vp, _sz, _vp, _vp]),
+    'gsn_csr_workspace_bytes': (ctypes.c_int, [_i64, _i64, _szp]),
+    'gsn_csr_build': (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    'gsn_mp_gin_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
+    'gsn_mp_ogb_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    'gsn_mp_segment_sum': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp]),
+    'gsn_mp_general_edge_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def so_path() -> str:
+    return _SO
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise RuntimeError(
+                f'{_SO} is missing: build the CUDA extension first (python -m gsn_b200.build). '
+                'gsn_b200 has no CPU or PyTorch fallback.')
+        L = ctypes.CDLL(_SO)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.gsn_abi_version() != 1:
+            raise RuntimeError('libgsn_b200.so ABI version mismatch; rebuild')
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != GSN_OK:
+        msg = _ERRORS.get(rc, str(rc))
+        if rc == -4:
+            msg += ': ' + (lib().gsn_last_cuda_error() or b'').decode()
+        raise RuntimeError(f'{what} failed: {msg}')
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor: gsn_b200 has no CPU path')
+
+
+def status_message(bits: int) -> str:
+    out = []
+    if bits & S_GRAPH_TOO_LARGE:
+        out.append('a graph has more vertices than the adjacency bitmask width allows')
+    if bits & S_CROSS_GRAPH_EDGE:
+        out.append('an edge joins two different graphs of the batch')
+    if bits & S_MISSING_EDGE:
+        out.append('a match used an edge (a,b) that is not a column of edge_index (asymmetric edge_index)')
+    if bits & S_INDEX_RANGE:
+        out.append('a node index is outside [0, num_nodes)')
+    return '; '.join(out)

@@ -1,0 +1,430 @@
+// MP kernels: CSR build + fused gather / concat / (transform) / segment-sum.
+//
+// Replaces the propagate() bodies of the reference's sparse layers
+// (graph_filters/GSN_sparse.py:122-176, GSN_edge_sparse.py:119-170,
+//  GSN_edge_sparse_ogb.py:86-129, MPNN_*.py): the [E,d] gathers, the
+// torch.cat of the message, the hybrid COO tensor [N,N,d] and
+// torch.sparse.sum(...).to_dense().
+//
+// Design: the aggregation index is grouped once per batch into a CSR whose rows
+// keep edge_index columns in ascending order, so every output row is reduced by
+// exactly one thread per feature chunk in a fixed order: no float atomics,
+// bit-reproducible run to run.  One thread owns one (row, VEC-wide column
+// chunk); consecutive threads own consecutive chunks of the same row, so the
+// neighbour-row gathers, the per-edge rows and the output row are all read /
+// written as full coalesced segments (float4 when widths allow).  Nothing of
+// size [E,d] is materialised for the gin / ogb kinds.
+#include "common.cuh"
+
+namespace gsn {
+
+// ------------------------------------------------------------------ CSR build
+__global__ void k_hist(const int64_t *__restrict__ key, int64_t E, int64_t N, int32_t *cnt, int32_t *status) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int64_t k = key[e];
+    if (k < 0 || k >= N) { atomicOr(status, GSN_S_INDEX_RANGE); return; }
+    atomicAdd(&cnt[k], 1);
+}
+
+__global__ void k_fill(const int64_t *__restrict__ key, int64_t E, int64_t N, const int32_t *__restrict__ rowptr,
+                       int32_t *cursor, int32_t *__restrict__ eid) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int64_t k = key[e];
+    if (k < 0 || k >= N) return;
+    int pos = atomicAdd(&cursor[k], 1);
+    eid[rowptr[k] + pos] = (int32_t)e;
+}
+
+// ascending edge ids inside every row (fixed summation order), then the gathered end point
+__global__ void k_sort_rows(const int32_t *__restrict__ rowptr, int64_t N, int32_t *eid,
+                            const int64_t *__restrict__ other, int32_t *__restrict__ nbr, int32_t *status,
+                            int64_t Nnodes) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int b = rowptr[r], e = rowptr[r + 1];
+    for (int i = b + 1; i < e; ++i) {
+        int v = eid[i], j = i - 1;
+        while (j >= b && eid[j] > v) { eid[j + 1] = eid[j]; --j; }
+        eid[j + 1] = v;
+    }
+    for (int i = b; i < e; ++i) {
+        int64_t o = other[eid[i]];
+        if (o < 0 || o >= Nnodes) { atomicOr(status, GSN_S_INDEX_RANGE); o = 0; }
+        nbr[i] = (int32_t)o;
+    }
+}
+
+// ------------------------------------------------------------------ vector helpers
+template <int VEC> struct Vec;
+template <> struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ static Vec ld(const float *p) { Vec r; r.v[0] = __ldg(p); return r; }
+    __device__ __forceinline__ void st(float *p) const { p[0] = v[0]; }
+};
+template <> struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ static Vec ld(const float *p) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+    }
+    __device__ __forceinline__ void st(float *p) const { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+constexpr int kMpThreads = 256;
+constexpr int kUnroll = 4;
+
+// ------------------------------------------------------------------ gin
+struct GinParams {
+    const int32_t *rowptr, *eid, *nbr;
+    int64_t N;
+    const float *eps;
+    float *out;
+    int n_segs, D;
+    GsnSegment seg[GSN_MAX_SEGMENTS];
+    int seg_off[GSN_MAX_SEGMENTS + 1];
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kMpThreads) gin_kernel(const __grid_constant__ GinParams p) {
+    const int D = p.D;
+    const int cpr = D / VEC;
+    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t row = t / cpr;
+    const int c = (int)(t % cpr) * VEC;
+    int si = 0;
+#pragma unroll
+    for (int i = 1; i < GSN_MAX_SEGMENTS; ++i)
+        if (i < p.n_segs && c >= p.seg_off[i]) si = i;
+    const GsnSegment &sg = p.seg[si];
+    const int col = c - p.seg_off[si];
+    const float one_eps = 1.0f + (p.eps ? __ldg(p.eps) : 0.0f);
+    float acc[VEC];
+    if (sg.self) {
+        Vec<VEC> s = Vec<VEC>::ld(sg.self + row * sg.self_ld + col);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = one_eps * (s.v[i] + sg.self_const);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = one_eps * sg.self_const;
+    }
+    if (sg.index_mode != 0) {
+        const float *src = sg.src;
+        const int ld = sg.src_ld;
+        const int32_t *idx = sg.index_mode == 1 ? p.nbr : p.eid;
+        int k = p.rowptr[row];
+        const int kend = p.rowptr[row + 1];
+        for (; k + kUnroll <= kend; k += kUnroll) {
+            int j[kUnroll];
+            Vec<VEC> m[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) j[u] = __ldg(idx + k + u);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) m[u] = Vec<VEC>::ld(src + (int64_t)j[u] * ld + col);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += m[u].v[i];
+        }
+        for (; k < kend; ++k) {
+            Vec<VEC> m = Vec<VEC>::ld(src + (int64_t)__ldg(idx + k) * ld + col);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] += m.v[i];
+        }
+    }
+    Vec<VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+    o.st(p.out + row * D + c);
+}
+
+// ------------------------------------------------------------------ ogb
+struct OgbParams {
+    const int32_t *rowptr, *eid, *nbr;
+    int64_t N;
+    const float *x, *id, *ef, *eps;
+    int d, id_per_edge;
+    float *out;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kMpThreads) ogb_kernel(const __grid_constant__ OgbParams p) {
+    const int cpr = p.d / VEC;
+    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t row = t / cpr;
+    const int c = (int)(t % cpr) * VEC;
+    const int d = p.d;
+    const float one_eps = 1.0f + (p.eps ? __ldg(p.eps) : 0.0f);
+    float acc[VEC];
+    {
+        Vec<VEC> s = Vec<VEC>::ld(p.x + row * d + c);
+        if (p.id && !p.id_per_edge) {
+            Vec<VEC> q = Vec<VEC>::ld(p.id + row * d + c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) s.v[i] += q.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = one_eps * s.v[i];
+    }
+    const int kend = p.rowptr[row + 1];
+    for (int k = p.rowptr[row]; k < kend; ++k) {
+        const int j = __ldg(p.nbr + k), e = __ldg(p.eid + k);
+        Vec<VEC> m = Vec<VEC>::ld(p.x + (int64_t)j * d + c);
+        if (p.id) {
+            Vec<VEC> q = Vec<VEC>::ld(p.id + (int64_t)(p.id_per_edge ? e : j) * d + c);
+            // reference order: (x_j + identifiers) + edge_features  (GSN_edge_sparse_ogb.py:122-125)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) m.v[i] += q.v[i];
+        }
+        Vec<VEC> f = Vec<VEC>::ld(p.ef + (int64_t)e * d + c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += fmaxf(m.v[i] + f.v[i], 0.0f);
+    }
+    Vec<VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+    o.st(p.out + row * d + c);
+}
+
+// ------------------------------------------------------------------ segment sum
+template <int VEC>
+__global__ void __launch_bounds__(kMpThreads)
+segsum_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ idx, int64_t N,
+              const float *__restrict__ msgs, int d, float *__restrict__ out) {
+    const int cpr = d / VEC;
+    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= N * cpr) return;
+    const int64_t row = t / cpr;
+    const int c = (int)(t % cpr) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+    int k = rowptr[row];
+    const int kend = rowptr[row + 1];
+    for (; k + kUnroll <= kend; k += kUnroll) {
+        int j[kUnroll];
+        Vec<VEC> m[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) j[u] = __ldg(idx + k + u);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) m[u] = Vec<VEC>::ld(msgs + (int64_t)j[u] * d + c);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] += m[u].v[i];
+    }
+    for (; k < kend; ++k) {
+        Vec<VEC> m = Vec<VEC>::ld(msgs + (int64_t)__ldg(idx + k) * d + c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += m.v[i];
+    }
+    Vec<VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+    o.st(out + row * d + c);
+}
+
+// ------------------------------------------------------------------ general (split first Linear)
+struct GenParams {
+    const int32_t *rowptr, *eid, *nbr;
+    int64_t N;
+    const float *P, *Q, *scale, *shift;
+    int dh, act;
+    float *S;
+    double *stats;
+};
+
+// choose_activation of models_misc.py:5-15
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case 0: return fmaxf(v, 0.0f);                       // relu
+        case 1: return v > 0.0f ? v : expm1f(v);             // elu (alpha = 1)
+        case 2: return tanhf(v);                             // tanh
+        default: return v;                                   // identity
+    }
+}
+
+template <int VEC, bool STATS>
+__global__ void __launch_bounds__(kMpThreads) general_edge_kernel(const __grid_constant__ GenParams p) {
+    extern __shared__ double sh_stats[];   // STATS: [2*dh]
+    const int dh = p.dh;
+    if (STATS) {
+        for (int i = threadIdx.x; i < 2 * dh; i += kMpThreads) sh_stats[i] = 0.0;
+        __syncthreads();
+    }
+    const int cpr = dh / VEC;
+    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    const bool active = t < p.N * cpr;
+    if (active) {
+        const int64_t row = t / cpr;
+        const int c = (int)(t % cpr) * VEC;
+        Vec<VEC> pi = Vec<VEC>::ld(p.P + row * (2 * dh) + c);
+        float sc[VEC], sf[VEC], acc[VEC];
+        double s1[VEC], s2[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            sc[i] = p.scale ? __ldg(p.scale + c + i) : 1.0f;
+            sf[i] = p.shift ? __ldg(p.shift + c + i) : 0.0f;
+            acc[i] = 0.0f;
+            s1[i] = 0.0;
+            s2[i] = 0.0;
+        }
+        const int kend = p.rowptr[row + 1];
+        for (int k = p.rowptr[row]; k < kend; ++k) {
+            const int j = __ldg(p.nbr + k);
+            Vec<VEC> pj = Vec<VEC>::ld(p.P + (int64_t)j * (2 * dh) + dh + c);
+            float h[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) h[i] = pi.v[i] + pj.v[i];
+            if (p.Q) {
+                Vec<VEC> q = Vec<VEC>::ld(p.Q + (int64_t)__ldg(p.eid + k) * dh + c);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) h[i] += q.v[i];
+            }
+            if (STATS) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { s1[i] += (double)h[i]; s2[i] += (double)h[i] * (double)h[i]; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += apply_act(fmaf(h[i], sc[i], sf[i]), p.act);
+            }
+        }
+        if (STATS) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                atomicAdd(&sh_stats[c + i], s1[i]);
+                atomicAdd(&sh_stats[dh + c + i], s2[i]);
+            }
+        } else {
+            Vec<VEC> o;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+            o.st(p.S + row * dh + c);
+        }
+    }
+    if (STATS) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * dh; i += kMpThreads)
+            if (sh_stats[i] != 0.0) atomicAdd(&p.stats[i], sh_stats[i]);
+    }
+}
+
+inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace gsn
+
+using namespace gsn;
+
+extern "C" int gsn_csr_workspace_bytes(int64_t N, int64_t E, size_t *bytes) {
+    if (!bytes || N < 0 || E < 0) return GSN_E_INVALID;
+    *bytes = align_up(sizeof(int32_t) * (size_t)(N + 8), 256) * 2 + align_up(sizeof(int32_t) * (size_t)(ceil_div(N + 1, 1024) + 8), 256);
+    return GSN_OK;
+}
+
+extern "C" int gsn_csr_build(const int64_t *d_key, const int64_t *d_other, int64_t E, int64_t N, int32_t *d_rowptr,
+                             int32_t *d_eid, int32_t *d_nbr, void *d_ws, size_t ws_bytes, int32_t *d_status,
+                             void *stream_) {
+    if (N < 0 || E < 0 || !d_rowptr || !d_ws || !d_status || (E > 0 && (!d_key || !d_other || !d_eid || !d_nbr)))
+        return GSN_E_INVALID;
+    if (N + 1 >= (int64_t)1 << 31 || E >= (int64_t)1 << 31) return GSN_E_UNSUPPORTED;
+    size_t need = 0;
+    gsn_csr_workspace_bytes(N, E, &need);
+    if (ws_bytes < need) return GSN_E_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t seg = align_up(sizeof(int32_t) * (size_t)(N + 8), 256);
+    int32_t *cnt = (int32_t *)d_ws;
+    int32_t *cursor = (int32_t *)((char *)d_ws + seg);
+    int32_t *scan_tmp = (int32_t *)((char *)d_ws + 2 * seg);
+    GSN_CUDA_OK(cudaMemsetAsync(d_ws, 0, 2 * seg, stream));
+    const int TB = 256;
+    if (E > 0) k_hist<<<(unsigned)ceil_div(E, TB), TB, 0, stream>>>(d_key, E, N, cnt, d_status);
+    int rc = exclusive_scan_i32(cnt, d_rowptr, N + 1, scan_tmp, stream);
+    if (rc) return rc;
+    if (E > 0) {
+        k_fill<<<(unsigned)ceil_div(E, TB), TB, 0, stream>>>(d_key, E, N, d_rowptr, cursor, d_eid);
+        k_sort_rows<<<(unsigned)ceil_div(N, TB), TB, 0, stream>>>(d_rowptr, N, d_eid, d_other, d_nbr, d_status, N);
+    }
+    GSN_LAUNCH_OK("gsn_csr_build");
+    return GSN_OK;
+}
+
+extern "C" int gsn_mp_gin_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                              int64_t E, const GsnSegment *h_segs, int32_t n_segs, const float *d_eps, float *d_out,
+                              void *stream_) {
+    if (N < 0 || E < 0 || !d_rowptr || !d_out || !h_segs || n_segs < 1 || n_segs > GSN_MAX_SEGMENTS) return GSN_E_INVALID;
+    GinParams p;
+    p.rowptr = d_rowptr; p.eid = d_eid; p.nbr = d_nbr; p.N = N; p.eps = d_eps; p.out = d_out; p.n_segs = n_segs;
+    int off = 0;
+    bool v4 = aligned16(d_out);
+    for (int i = 0; i < n_segs; ++i) {
+        const GsnSegment &sg = h_segs[i];
+        if (sg.width < 1 || (sg.index_mode != 0 && !sg.src) || sg.index_mode < 0 || sg.index_mode > 2) return GSN_E_INVALID;
+        p.seg[i] = sg;
+        p.seg_off[i] = off;
+        off += sg.width;
+        v4 = v4 && sg.width % 4 == 0 && (sg.index_mode == 0 || (sg.src_ld % 4 == 0 && aligned16(sg.src))) &&
+             (!sg.self || (sg.self_ld % 4 == 0 && aligned16(sg.self)));
+    }
+    for (int i = n_segs; i <= GSN_MAX_SEGMENTS; ++i) p.seg_off[i] = off;
+    p.D = off;
+    if (N == 0) return GSN_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (v4) gin_kernel<4><<<(unsigned)ceil_div(N * (off / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
+    else gin_kernel<1><<<(unsigned)ceil_div(N * (int64_t)off, kMpThreads), kMpThreads, 0, stream>>>(p);
+    GSN_LAUNCH_OK("gsn_mp_gin_fwd");
+    return GSN_OK;
+}
+
+extern "C" int gsn_mp_ogb_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                              int64_t E, const float *d_x, const float *d_id, int32_t id_per_edge, const float *d_ef,
+                              int32_t d, const float *d_eps, float *d_out, void *stream_) {
+    if (N < 0 || E < 0 || d < 1 || !d_rowptr || !d_x || !d_ef || !d_out) return GSN_E_INVALID;
+    if (N == 0) return GSN_OK;
+    OgbParams p{d_rowptr, d_eid, d_nbr, N, d_x, d_id, d_ef, d_eps, d, id_per_edge, d_out};
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool v4 = d % 4 == 0 && aligned16(d_x) && aligned16(d_id) && aligned16(d_ef) && aligned16(d_out);
+    if (v4) ogb_kernel<4><<<(unsigned)ceil_div(N * (d / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
+    else ogb_kernel<1><<<(unsigned)ceil_div(N * d, kMpThreads), kMpThreads, 0, stream>>>(p);
+    GSN_LAUNCH_OK("gsn_mp_ogb_fwd");
+    return GSN_OK;
+}
+
+extern "C" int gsn_mp_segment_sum(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                                  int64_t E, const float *d_msgs, int32_t d, int32_t gather, float *d_out,
+                                  void *stream_) {
+    if (N < 0 || E < 0 || d < 1 || !d_rowptr || !d_out || (E > 0 && !d_msgs)) return GSN_E_INVALID;
+    if (N == 0) return GSN_OK;
+    const int32_t *idx = gather ? d_nbr : d_eid;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool v4 = d % 4 == 0 && aligned16(d_msgs) && aligned16(d_out);
+    if (v4) segsum_kernel<4><<<(unsigned)ceil_div(N * (d / 4), kMpThreads), kMpThreads, 0, stream>>>(d_rowptr, idx, N, d_msgs, d, d_out);
+    else segsum_kernel<1><<<(unsigned)ceil_div(N * d, kMpThreads), kMpThreads, 0, stream>>>(d_rowptr, idx, N, d_msgs, d, d_out);
+    GSN_LAUNCH_OK("gsn_mp_segment_sum");
+    return GSN_OK;
+}
+
+extern "C" int gsn_mp_general_edge_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                                       int64_t E, const float *d_P, const float *d_Q, int32_t dh,
+                                       const float *d_scale, const float *d_shift, int32_t act, float *d_S,
+                                       double *d_stats, void *stream_) {
+    if (N < 0 || E < 0 || dh < 1 || !d_rowptr || !d_P || (!d_S && !d_stats)) return GSN_E_INVALID;
+    if (N == 0) return GSN_OK;
+    GenParams p{d_rowptr, d_eid, d_nbr, N, d_P, d_Q, d_scale, d_shift, dh, act, d_S, d_stats};
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool v4 = dh % 4 == 0 && aligned16(d_P) && aligned16(d_Q) && aligned16(d_S);
+    const size_t smem = d_stats ? sizeof(double) * 2 * (size_t)dh : 0;
+    const int64_t threads = N * (v4 ? dh / 4 : dh);
+    const unsigned grid = (unsigned)ceil_div(threads, kMpThreads);
+    if (d_stats) {
+        if (v4) general_edge_kernel<4, true><<<grid, kMpThreads, smem, stream>>>(p);
+        else general_edge_kernel<1, true><<<grid, kMpThreads, smem, stream>>>(p);
+    } else {
+        if (v4) general_edge_kernel<4, false><<<grid, kMpThreads, smem, stream>>>(p);
+        else general_edge_kernel<1, false><<<grid, kMpThreads, smem, stream>>>(p);
+    }
+    GSN_LAUNCH_OK("gsn_mp_general_edge_fwd");
+    return GSN_OK;
+}

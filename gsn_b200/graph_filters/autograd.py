@@ -1,0 +1,105 @@
+"""Differentiable (training) path of the sparse layers.
+
+The inference path (base.py) fuses gather+concat+transform+sum into single
+kernels.  Training needs gradients w.r.t. x, identifiers, edge features and the
+MLP weights; here the scatter-add and the row gather are autograd Functions
+backed by the library's deterministic segment-sum (forward AND backward: the
+backward of a gather is a segment-sum over the transposed grouping, the backward
+of a segment-sum is a gather), and the message is formed as in the reference
+(graph_filters/GSN_edge_sparse.py:152-170 etc.) so that BatchNorm inside msg_fn
+sees the same E rows.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+class _SegmentSum(torch.autograd.Function):
+    """out[i] = sum_{e: key(e)=i} msgs[e]   (torch.sparse.sum(...).to_dense(), GSN_sparse.py:143)"""
+
+    @staticmethod
+    def forward(ctx, msgs, plan):
+        ctx.plan = plan
+        return ops.segment_sum(plan, msgs)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        plan = ctx.plan
+        key = plan.edge_index[plan.select]
+        return grad_out.contiguous().index_select(0, key), None
+
+
+class _GatherRows(torch.autograd.Function):
+    """rows[e] = x[index(e)] with index = edge_index[row]; backward is a
+    deterministic segment-sum grouped by that index."""
+
+    @staticmethod
+    def forward(ctx, x, edge_index, row, num_nodes):
+        ctx.args = (edge_index, row, num_nodes)
+        return x.index_select(0, edge_index[row])
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        edge_index, row, num_nodes = ctx.args
+        flow = 'target_to_source' if row == 0 else 'source_to_target'
+        plan = ops.edge_plan(edge_index, num_nodes, flow)       # grouped by edge_index[row]
+        return ops.segment_sum(plan, grad_rows.contiguous()), None, None, None
+
+
+def segment_sum(msgs, plan):
+    return _SegmentSum.apply(msgs, plan)
+
+
+def gather_rows(x, edge_index, row):
+    return _GatherRows.apply(x, edge_index, row, x.shape[0])
+
+
+def forward_with_grad(layer, x, edge_index, identifiers, ef):
+    n = x.shape[0]
+    plan = ops.edge_plan(edge_index, n, layer.flow)
+    sel = plan.select
+    x = x.float()
+    x_j = gather_rows(x, edge_index, 1 - sel)
+    local = layer.id_scope == 'local'
+    if layer.msg_kind == 'gin':
+        self_parts, msg_parts = [x], [x_j]
+        if layer.uses_ids:
+            if local:
+                id_ii, id_nb = layer.central_node_id_encoder(identifiers, n)
+                self_parts.append(id_ii)
+                msg_parts.append(id_nb)
+            else:
+                self_parts.append(identifiers)
+                msg_parts.append(gather_rows(identifiers.float(), edge_index, 1 - sel))
+        if layer.uses_ef:
+            ef_ii, ef_nb = layer.central_node_edge_encoder(ef, n)
+            self_parts.append(ef_ii)
+            msg_parts.append(ef_nb)
+        agg = segment_sum(torch.cat(msg_parts, -1).float(), plan)
+        return layer.update_fn((1 + layer.eps) * torch.cat(self_parts, -1) + agg)
+    if layer.msg_kind == 'ogb':
+        self_msg = x
+        m = x_j
+        if layer.uses_ids:
+            if local:
+                m = m + identifiers
+            else:
+                self_msg = x + identifiers
+                m = m + gather_rows(identifiers.float(), edge_index, 1 - sel)
+        m = torch.relu(m + ef)
+        return layer.update_fn((1 + layer.eps) * self_msg + segment_sum(m, plan))
+    # general
+    x_i = gather_rows(x, edge_index, sel)
+    parts = [x_i, x_j]
+    if layer.uses_ids:
+        if local:
+            parts.append(identifiers.float())
+        else:
+            idf = identifiers.float()
+            parts += [gather_rows(idf, edge_index, sel), gather_rows(idf, edge_index, 1 - sel)]
+    if layer.uses_ef:
+        parts.append(ef.float())
+    msgs = layer.msg_fn(torch.cat(parts, -1))
+    return layer.update_fn(torch.cat((x, segment_sum(msgs, plan)), -1))

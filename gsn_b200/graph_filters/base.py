@@ -1,0 +1,184 @@
+"""Shared implementation of the six sparse layers.
+
+One class covers GSN_sparse / GSN_edge_sparse / GSN_edge_sparse_ogb and their
+MPNN_* twins (= the same layer without identifiers): the reference
+repeats one propagate() skeleton six times
+(graph_filters/GSN_sparse.py:122-154, GSN_edge_sparse.py:119-150,
+ GSN_edge_sparse_ogb.py:86-117, MPNN_sparse.py:91-115, MPNN_edge_sparse.py:110-134,
+ MPNN_edge_sparse_ogb.py:81-106).
+
+forward(x, edge_index, identifiers=, degrees=, edge_features=) keeps the
+reference's meaning; the gather/concat/scatter-add runs in libgsn_b200.so:
+
+  gin      one fused kernel: (1+eps)*cat(x, id_ii, ef_ii) + sum_j cat(x_j, id, ef)
+  ogb      one fused kernel: (1+eps)*(x [+id]) + sum_j relu(x_j + id + e_ij)
+  general  msg_fn's first Linear is split over its inputs
+           (W1 [x_i|x_j|ids|ef] = P_i[i] + P_j[j] + Q[e]) so its GEMM runs on N
+           rows instead of E; one fused kernel does gather-add-BN-act-segment-sum;
+           the second Linear commutes with the sum: sum_e (W2 h_e + b2) = W2 S + deg*b2.
+
+aggr='mean' raises NameError in every reference layer; here it
+raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..encoders import central_encoder
+from ..models_misc import mlp
+
+
+class SparseFilter(nn.Module):
+
+    def _configure(self, *, d_in, d_degree, degree_as_tag, retain_features, d_msg, d_up, d_h, seed,
+                   activation_name, bn, aggr, msg_kind, eps, train_eps, flow, d_ef=None, d_id=None,
+                   id_scope=None, extras=None):
+        extras = extras or {}
+        self.flow, self.aggr, self.msg_kind, self.id_scope = flow, aggr, msg_kind, id_scope
+        self.degree_as_tag, self.retain_features = degree_as_tag, retain_features
+        self.uses_ids, self.uses_ef = d_id is not None, d_ef is not None
+        self.activation_name = activation_name
+        d_id = d_id if self.uses_ids else 0
+        d_ef = d_ef if self.uses_ef else 0
+
+        d_msg = d_in if d_msg is None else d_msg
+        if degree_as_tag:
+            d_in = d_in + d_degree if retain_features else d_degree
+
+        if msg_kind == 'gin':
+            if self.uses_ef:
+                self.central_node_edge_encoder = central_encoder(extras['edge_embedding'], d_ef,
+                                                                 extend=extras['extend_dims'])
+                d_ef = self.central_node_edge_encoder.d_out
+            if self.uses_ids and id_scope == 'local':
+                self.central_node_id_encoder = central_encoder(extras['id_embedding'], d_id,
+                                                               extend=extras['extend_dims'])
+                d_id = self.central_node_id_encoder.d_out
+            self._make_eps(eps, train_eps)
+            self.msg_fn = None
+            update_input_dim = d_in + d_id + d_ef
+        elif msg_kind == 'general':
+            n_id = d_id if id_scope == 'local' else 2 * d_id
+            self.msg_fn = mlp(2 * d_in + n_id + d_ef, d_msg, d_h, seed, activation_name, bn)
+            update_input_dim = d_in + d_msg
+        elif msg_kind == 'ogb':
+            self._make_eps(eps, train_eps)
+            update_input_dim = d_in
+        else:
+            raise NotImplementedError('msg kind {} is not currently supported.'.format(msg_kind))
+        self.update_fn = mlp(update_input_dim, d_up, d_h, seed, activation_name, bn)
+        self._dims = (d_in, d_id, d_ef)
+
+    def _make_eps(self, eps, train_eps):
+        self.initial_eps = eps
+        if train_eps:
+            self.eps = nn.Parameter(torch.Tensor([eps]))
+        else:
+            self.register_buffer('eps', torch.Tensor([eps]))
+        self.eps.data.fill_(self.initial_eps)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, edge_index, **kwargs):
+        x = x.unsqueeze(-1) if x.dim() == 1 else x
+        degrees = kwargs['degrees']
+        degrees = degrees.unsqueeze(-1) if degrees.dim() == 1 else degrees
+        if self.degree_as_tag:
+            x = torch.cat([x, degrees], -1) if self.retain_features else degrees
+        identifiers = kwargs.get('identifiers') if self.uses_ids else None
+        if self.uses_ids and identifiers.dim() == 1:
+            identifiers = identifiers.unsqueeze(-1)
+        ef = None
+        if self.uses_ef:
+            ef = kwargs['edge_features']
+            ef = ef.unsqueeze(-1) if ef.dim() == 1 else ef
+        if self.aggr != 'add':
+            if self.aggr == 'mean':
+                raise NotImplementedError("aggr='mean' is unreachable in the reference (NameError: aggr_index)")
+            raise NotImplementedError('Aggregation kind {} is not currently supported.'.format(self.aggr))
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import forward_with_grad
+            return forward_with_grad(self, x, edge_index, identifiers, ef)
+        plan = ops.edge_plan(edge_index, x.shape[0], self.flow)
+        if self.msg_kind == 'gin':
+            return self.update_fn(self._gin(plan, x, identifiers, ef))
+        if self.msg_kind == 'ogb':
+            return self.update_fn(ops.ogb_aggregate(plan, x, identifiers, self.id_scope == 'local', ef, self.eps))
+        return self._general(plan, x, identifiers, ef)
+
+    # ------------------------------------------------------------------ gin
+    def _gin_segments(self, x, identifiers, ef):
+        segs = [dict(width=x.shape[1], src=x, mode=ops.MODE_NBR, self=x)]
+
+        def per_edge(enc: central_encoder, rows):
+            if enc.extend and enc.one_hot:          # extra one-hot column: neighbours 0, centre 1
+                segs.append(dict(width=1, src=None, mode=ops.MODE_NONE, const=1.0))
+            segs.append(dict(width=rows.shape[1], src=rows, mode=ops.MODE_EDGE, self=enc.central_row()))
+
+        if self.uses_ids:
+            if self.id_scope == 'local':
+                per_edge(self.central_node_id_encoder, identifiers)
+            else:
+                segs.append(dict(width=identifiers.shape[1], src=identifiers, mode=ops.MODE_NBR, self=identifiers))
+        if self.uses_ef:
+            per_edge(self.central_node_edge_encoder, ef)
+        return segs
+
+    def _gin(self, plan, x, identifiers, ef):
+        return ops.gin_aggregate(plan, self._gin_segments(x.float(), identifiers, ef), self.eps)
+
+    # ------------------------------------------------------------------ general
+    def _split_first_linear(self, d_in, d_id, d_ef):
+        """column blocks of msg_fn.fc[0].weight in the order of the reference's
+        torch.cat: (x_i, x_j, id_i, id_j | id_ij, ef)"""
+        W = self.msg_fn.fc[0].weight
+        o = 0
+        Wxi = W[:, o:o + d_in]; o += d_in
+        Wxj = W[:, o:o + d_in]; o += d_in
+        Wii = Wij = Wq_id = None
+        if self.uses_ids:
+            if self.id_scope == 'local':
+                Wq_id = W[:, o:o + d_id]; o += d_id
+            else:
+                Wii = W[:, o:o + d_id]; o += d_id
+                Wij = W[:, o:o + d_id]; o += d_id
+        Wq_ef = W[:, o:o + d_ef] if self.uses_ef else None
+        return Wxi, Wxj, Wii, Wij, Wq_id, Wq_ef
+
+    def _general(self, plan, x, identifiers, ef):
+        f = self.msg_fn
+        if f.depth != 2:
+            raise NotImplementedError('general message kind: msg_fn with num_mlp_layers != 2 is not built yet')
+        x = x.float()
+        d_in = x.shape[1]
+        d_id = identifiers.shape[1] if self.uses_ids else 0
+        d_ef = ef.shape[1] if self.uses_ef else 0
+        Wxi, Wxj, Wii, Wij, Wq_id, Wq_ef = self._split_first_linear(d_in, d_id, d_ef)
+        b1 = f.fc[0].bias
+        # P = [x W_xi^T + id W_ii^T + b1 | x W_xj^T + id W_ij^T]   (N rows)
+        P = torch.addmm(torch.cat((b1, torch.zeros_like(b1))), x, torch.cat((Wxi, Wxj), 0).t())
+        if Wii is not None:
+            P.addmm_(identifiers.float(), torch.cat((Wii, Wij), 0).t())
+        # Q = [id_ij | ef] W_q^T                                   (E rows, narrow K)
+        Q = None
+        if Wq_id is not None:
+            Q = identifiers.float() @ Wq_id.t()
+        if Wq_ef is not None:
+            Q = ef.float() @ Wq_ef.t() if Q is None else Q.addmm_(ef.float(), Wq_ef.t())
+        stats = None
+        if f.batch_norm and f.bn[0].training:
+            st = ops.general_edge_stats(plan, P, Q)
+            cnt = max(plan.E, 1)
+            mean = st[0] / cnt
+            var = (st[1] / cnt - mean * mean).clamp_min_(0)
+            stats = (mean, var, plan.E)
+        scale, shift = f.bn_affine(0, stats)
+        S = ops.general_edge(plan, P, Q, scale, shift, self.activation_name)
+        W2, b2 = f.fc[1].weight, f.fc[1].bias
+        agg = torch.addmm(torch.outer(plan.degree(), b2), S, W2.t())
+        return self.update_fn(torch.cat((x, agg), -1))
+
+    def __repr__(self):
+        return '{}(msg_fn = {}, update_fn = {})'.format(self.__class__.__name__, getattr(self, 'msg_fn', None),
+                                                        self.update_fn)

@@ -1,0 +1,216 @@
+"""MP operators: thin PyTorch-tensor front-ends of the C ABI (include/gsn_b200.h).
+
+`EdgePlan` is the once-per-batch grouping of edge_index by aggregation index; it
+replaces the COO tensor + torch.sparse.sum coalesce the reference redoes in every
+layer (graph_filters/GSN_sparse.py:140-143).  The three fused forward operators
+replace propagate()+message() of the reference layers; see csrc/mp_kernels.cu.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+class GsnSegment(ctypes.Structure):
+    """ctypes image of `struct GsnSegment` (include/gsn_b200.h)."""
+    _fields_ = [('src', ctypes.c_void_p), ('self_', ctypes.c_void_p), ('width', ctypes.c_int32),
+                ('src_ld', ctypes.c_int32), ('self_ld', ctypes.c_int32), ('index_mode', ctypes.c_int32),
+                ('self_const', ctypes.c_float), ('_pad', ctypes.c_int32)]
+
+
+MODE_NONE, MODE_NBR, MODE_EDGE = 0, 1, 2
+
+
+def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    _lib.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class EdgePlan:
+    """CSR of edge_index grouped by the aggregation index.
+
+    flow='source_to_target' (the CLI default, main.py:618): select = 1, i.e.
+    messages are summed at edge_index[1] and x_j is gathered at edge_index[0]
+    (GSN_sparse.py:125-129)."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, flow: str = 'source_to_target'):
+        _lib.require_cuda(edge_index, 'edge_index')
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError('edge_index must be int64 [2, E]')
+        ei = edge_index.contiguous()
+        select = 0 if flow == 'target_to_source' else 1
+        self.select = select
+        self.N, self.E = int(num_nodes), int(ei.shape[1])
+        dev = ei.device
+        self.device = dev
+        self.edge_index = ei
+        self.rowptr = torch.empty(self.N + 1, dtype=torch.int32, device=dev)
+        self.eid = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
+        self.nbr = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        nb = ctypes.c_size_t(0)
+        _lib.check(L.gsn_csr_workspace_bytes(self.N, self.E, ctypes.byref(nb)), 'gsn_csr_workspace_bytes')
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        key, other = ei[select], ei[1 - select]
+        with torch.cuda.device(dev):
+            _lib.check(L.gsn_csr_build(_lib.ptr(key), _lib.ptr(other), self.E, self.N, _lib.ptr(self.rowptr),
+                                       _lib.ptr(self.eid), _lib.ptr(self.nbr), _lib.ptr(ws), nb.value,
+                                       _lib.ptr(self.status), _lib.stream_ptr()), 'gsn_csr_build')
+        self._ws = ws           # keep alive until the stream has consumed it
+        self._transposed: Optional['EdgePlan'] = None
+        self._deg: Optional[torch.Tensor] = None
+
+    def degree(self) -> torch.Tensor:
+        """number of aggregated messages per node, float32 [N]"""
+        if self._deg is None:
+            self._deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)
+        return self._deg
+
+    def raise_on_status(self):
+        bits = int(self.status.item())
+        if bits:
+            raise IndexError(_lib.status_message(bits))
+
+
+_plan_cache: List[Tuple[tuple, EdgePlan]] = []
+_PLAN_CACHE_SIZE = 8
+
+
+def edge_plan(edge_index: torch.Tensor, num_nodes: int, flow: str = 'source_to_target') -> EdgePlan:
+    """Cached EdgePlan: the layers of one model see the same edge_index tensor, so
+    the CSR is built once per batch, not once per layer."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), flow,
+           edge_index.device.index)
+    for k, p in _plan_cache:
+        if k == key and p.edge_index.data_ptr() == edge_index.data_ptr():
+            return p
+    p = EdgePlan(edge_index, num_nodes, flow)
+    _plan_cache.append((key, p))
+    if len(_plan_cache) > _PLAN_CACHE_SIZE:
+        _plan_cache.pop(0)
+    return p
+
+
+def clear_plan_cache():
+    _plan_cache.clear()
+
+
+# ----------------------------------------------------------------------------
+def gin_aggregate(plan: EdgePlan, segments: Sequence[dict], eps: Optional[torch.Tensor]) -> torch.Tensor:
+    """out[i] = (1+eps) * cat_s(self_s[i] + const_s) + sum_{e -> i} cat_s(src_s[index_s(e)]).
+
+    segments: dicts with keys width, src (tensor or None), mode (MODE_*), self
+    (tensor [N,w], [1,w]/[w] broadcast, or None), const (float)."""
+    segs = (GsnSegment * len(segments))()
+    keep = []
+    D = 0
+    for i, s in enumerate(segments):
+        w = int(s['width'])
+        src = _f32c(s.get('src'), 'segment src')
+        slf = _f32c(s.get('self'), 'segment self')
+        mode = int(s.get('mode', MODE_NONE))
+        if src is None:
+            mode = MODE_NONE
+        segs[i].width = w
+        segs[i].index_mode = mode
+        segs[i].self_const = float(s.get('const', 0.0))
+        if src is not None:
+            if src.dim() != 2 or src.shape[1] != w:
+                raise ValueError(f'segment {i}: src must be [rows, {w}]')
+            want = plan.N if mode == MODE_NBR else plan.E
+            if src.shape[0] != want:
+                raise ValueError(f'segment {i}: src has {src.shape[0]} rows, expected {want}')
+            segs[i].src = src.data_ptr()
+            segs[i].src_ld = w
+            keep.append(src)
+        if slf is not None:
+            if slf.numel() == w:
+                segs[i].self_ld = 0
+            elif slf.dim() == 2 and slf.shape == (plan.N, w):
+                segs[i].self_ld = w
+            else:
+                raise ValueError(f'segment {i}: self must be [N,{w}] or [{w}]')
+            segs[i].self_ = slf.data_ptr()
+            keep.append(slf)
+        D += w
+    out = torch.empty((plan.N, D), dtype=torch.float32, device=plan.device)
+    eps_t = _f32c(eps, 'eps')
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.lib().gsn_mp_gin_fwd(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N,
+                                             plan.E, ctypes.cast(segs, ctypes.c_void_p), len(segments),
+                                             _lib.ptr(eps_t), _lib.ptr(out), _lib.stream_ptr()), 'gsn_mp_gin_fwd')
+    return out
+
+
+def ogb_aggregate(plan: EdgePlan, x: torch.Tensor, identifiers: Optional[torch.Tensor], id_per_edge: bool,
+                  edge_features: torch.Tensor, eps: Optional[torch.Tensor]) -> torch.Tensor:
+    """(1+eps)*(x [+ id]) + sum_e relu(x_j + id + e_ij)  (GSN_edge_sparse_ogb.py:75-84,119-126)."""
+    x = _f32c(x, 'x')
+    idt = _f32c(identifiers, 'identifiers')
+    ef = _f32c(edge_features, 'edge_features')
+    d = x.shape[1]
+    if ef.shape != (plan.E, d) or (idt is not None and idt.shape != ((plan.E if id_per_edge else plan.N), d)):
+        raise ValueError('ogb message kind needs x, identifiers and edge_features of equal width')
+    out = torch.empty((plan.N, d), dtype=torch.float32, device=plan.device)
+    eps_t = _f32c(eps, 'eps')
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.lib().gsn_mp_ogb_fwd(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N,
+                                             plan.E, _lib.ptr(x), _lib.ptr(idt), int(bool(id_per_edge)), _lib.ptr(ef),
+                                             d, _lib.ptr(eps_t), _lib.ptr(out), _lib.stream_ptr()), 'gsn_mp_ogb_fwd')
+    return out
+
+
+def segment_sum(plan: EdgePlan, rows: torch.Tensor, gather_neighbour: bool = False) -> torch.Tensor:
+    """out[i] = sum_{e -> i} rows[e]   (or rows[nbr(e)] with gather_neighbour)."""
+    rows = _f32c(rows, 'rows')
+    d = rows.shape[1]
+    out = torch.empty((plan.N, d), dtype=torch.float32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.lib().gsn_mp_segment_sum(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr),
+                                                 plan.N, plan.E, _lib.ptr(rows), d, int(bool(gather_neighbour)),
+                                                 _lib.ptr(out), _lib.stream_ptr()), 'gsn_mp_segment_sum')
+    return out
+
+
+ACTIVATIONS = {'relu': 0, 'elu': 1, 'tanh': 2, 'identity': 3}
+
+
+def general_edge(plan: EdgePlan, P: torch.Tensor, Q: Optional[torch.Tensor], scale: Optional[torch.Tensor],
+                 shift: Optional[torch.Tensor], activation: str = 'relu') -> torch.Tensor:
+    """S[i] = sum_{e -> i} act((P[i,:dh] + P[nbr(e),dh:] + Q[e]) * scale + shift)."""
+    P = _f32c(P, 'P')
+    Q = _f32c(Q, 'Q')
+    dh = P.shape[1] // 2
+    S = torch.empty((plan.N, dh), dtype=torch.float32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.lib().gsn_mp_general_edge_fwd(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr),
+                                                      plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), dh,
+                                                      _lib.ptr(_f32c(scale, 'scale')), _lib.ptr(_f32c(shift, 'shift')),
+                                                      ACTIVATIONS[activation], _lib.ptr(S), None,
+                                                      _lib.stream_ptr()), 'gsn_mp_general_edge_fwd')
+    return S
+
+
+def general_edge_stats(plan: EdgePlan, P: torch.Tensor, Q: Optional[torch.Tensor]) -> torch.Tensor:
+    """Per-channel [sum, sum of squares] of h_e = P_i + P_j + Q_e over all edges
+    (float64 [2, dh]): the batch statistics BatchNorm1d needs in training mode
+    (models_misc.py:54-55 runs BN over the E message rows)."""
+    P = _f32c(P, 'P')
+    Q = _f32c(Q, 'Q')
+    dh = P.shape[1] // 2
+    stats = torch.zeros((2, dh), dtype=torch.float64, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.lib().gsn_mp_general_edge_fwd(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr),
+                                                      plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), dh, None, None, 3,
+                                                      None, _lib.ptr(stats), _lib.stream_ptr()),
+                   'gsn_mp_general_edge_fwd')
+    return stats

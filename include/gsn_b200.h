@@ -1,0 +1,224 @@
+/*
+ * gsn_b200 -- C ABI of libgsn_b200.so (sm_100a).
+ *
+ * The reference (gbouritsas/GSN) is pure Python and has no FFI; these entry
+ * points are what a ctypes binding added to the reference would call for its
+ * two data-parallel hot paths (INTEGRATION.md shows the stubs):
+ *
+ *   COUNT  utils_graph_processing.py:103-179 + utils_ids.py:7-29
+ *          (graph-tool subgraph_isomorphism + the Python per-map loops)
+ *   MP     graph_filters/GSN_sparse.py:122-176, GSN_edge_sparse.py:119-170,
+ *          GSN_edge_sparse_ogb.py:86-129 and the MPNN_* twins
+ *          (gather -> concat structural ids -> [transform] -> scatter-add)
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller; h_* is host
+ *     memory.  The library never allocates, frees or retains caller memory.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises unless its comment says so.
+ *   - return value: 0 = enqueued / ok, <0 = GSN_E_* (argument or CUDA error
+ *     detected on the host).  Data-dependent errors (a graph larger than the
+ *     bitmask width, an edge joining two graphs, an asymmetric edge hit by a
+ *     match -- the reference's KeyError) are written to the caller's
+ *     `d_status` word (int32, device) as GSN_S_* bits; the caller reads it when
+ *     it next synchronises.
+ *   - no C++ exceptions cross this boundary; reentrant; no global mutable state.
+ *   - edge_index is the reference's layout: int64 [2,E] row-major, row 0 =
+ *     source, row 1 = target, GLOBAL (batched) node ids.
+ */
+#ifndef GSN_B200_H_
+#define GSN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSN_ABI_VERSION 1
+
+/* host-side return codes */
+#define GSN_OK 0
+#define GSN_E_INVALID (-1)      /* bad argument */
+#define GSN_E_UNSUPPORTED (-2)  /* shape outside the built kernels */
+#define GSN_E_WORKSPACE (-3)    /* workspace too small */
+#define GSN_E_CUDA (-4)         /* a CUDA runtime call failed; see gsn_last_cuda_error */
+
+/* device-side status bits (OR-ed into *d_status) */
+#define GSN_S_GRAPH_TOO_LARGE 1 /* a graph has more than 64*W vertices */
+#define GSN_S_CROSS_GRAPH_EDGE 2/* an edge joins two graphs of the batch */
+#define GSN_S_MISSING_EDGE 4    /* edge scope: a match used (a,b) but edge_index has no column (a,b)
+                                   (utils_graph_processing.py:173 raises KeyError) */
+#define GSN_S_INDEX_RANGE 8     /* a node id outside [0,N) */
+
+#define GSN_MAXK 16             /* max pattern vertices */
+
+/* ------------------------------------------------------------------ */
+/* COUNT                                                               */
+/* ------------------------------------------------------------------ */
+
+/*
+ * Matching plan of one pattern H, compiled on the host (gsn_b200/patterns.py)
+ * from the output of automorphism_orbits / induced_edge_automorphism_orbits
+ * (utils_graph_processing.py:10-100).  Positions 0..k-1 are pattern vertices in
+ * matching order; position 1 is adjacent to position 0; every position p>=1 has
+ * at least one earlier neighbour.  The gt constraints break Aut(H) so that each
+ * occurrence (class of |Aut(H)| maps) is enumerated exactly once, which equals
+ * the reference's "count every map, divide by aut_count" (:127, :175).
+ */
+typedef struct GsnPlan {
+    int32_t k;                       /* pattern vertices, 2..GSN_MAXK */
+    int32_t induced;                 /* 0: monomorphisms, 1: induced  (:116 / :156) */
+    int32_t scope;                   /* 0: vertex counts (:103), 1: edge counts (:134) */
+    int32_t n_cols;                  /* orbits of this pattern = output columns */
+    int32_t col0;                    /* first output column of this pattern */
+    int32_t family;                  /* GSN_FAMILY_* */
+    int32_t kmin, kmax;              /* GSN_FAMILY_CYCLES/CLIQUES: sizes kmin..kmax, one column each */
+    uint32_t nbr_mask[GSN_MAXK];     /* bit q (q<p): positions q,p adjacent in H */
+    uint32_t non_mask[GSN_MAXK];     /* bit q (q<p): positions q,p NOT adjacent in H */
+    uint32_t gt_mask[GSN_MAXK];      /* bit q (q<p): require f(q) < f(p) */
+    int8_t vorbit[GSN_MAXK];         /* vertex scope: orbit (column) of position p */
+    int8_t e_fwd[GSN_MAXK][GSN_MAXK];/* edge scope: [p][q], q<p: orbit of directed pattern edge q->p, -1 none */
+    int8_t e_bwd[GSN_MAXK][GSN_MAXK];/* edge scope: [p][q], q<p: orbit of directed pattern edge p->q, -1 none */
+} GsnPlan;
+
+#define GSN_FAMILY_GENERIC 0
+#define GSN_FAMILY_CYCLES 1      /* all cycle lengths kmin..kmax in one traversal */
+#define GSN_FAMILY_CLIQUES 2     /* all clique sizes kmin..kmax in one traversal */
+
+/*
+ * Bytes of device workspace gsn_graph_build needs for a batch with N nodes, E
+ * edge_index columns and W 64-bit adjacency words per vertex
+ * (W >= ceil(max graph size / 64)).
+ */
+int gsn_graph_workspace_bytes(int64_t N, int64_t E, int32_t W, size_t *bytes);
+
+/*
+ * Builds the batched simple undirected graph the reference builds per graph with
+ *   gt.Graph(directed=False); add_edge_list; remove_self_loops; remove_parallel_edges
+ * (utils_graph_processing.py:110-113, :150-153): per-vertex adjacency bitmasks,
+ * slot offsets (CSR of the simple graph, neighbours ascending) and the
+ * edge_dict of :142-144 (slot -> LAST edge_index column holding that pair).
+ *   d_node_ptr  int64 [G+1]  first node of every graph (PyG batch.ptr)
+ */
+int gsn_graph_build(const int64_t *d_edge_index, int64_t E, const int64_t *d_node_ptr, int64_t G,
+                    int64_t N, int32_t W, void *d_ws, size_t ws_bytes, int32_t *d_status, void *stream);
+
+/* Bytes of scratch gsn_count_pattern needs (edge scope: per-slot accumulators). */
+int gsn_count_scratch_bytes(int64_t N, int64_t E, const GsnPlan *h_plan, size_t *bytes);
+
+/*
+ * Replaces count_fn(edge_index, subgraph_dict=, induced=, num_nodes=) of
+ * utils_ids.py:24 for the whole batch in one launch:
+ *   scope 0: d_out[v, col0+o] = #occurrences of H in which vertex v plays orbit o   (:103-131)
+ *   scope 1: d_out[e, col0+o] = #occurrences in which edge_index column e plays
+ *            edge orbit o; rows follow edge_index columns, duplicate columns ->
+ *            last one wins, self loops -> 0                                       (:134-179)
+ * d_out is int64 [rows, out_ld] (identifiers after .long(), utils_ids.py:27);
+ * the columns [col0, col0+n_cols) are overwritten.
+ * d_ws must come from gsn_graph_build on the same (edge_index, node_ptr).
+ */
+int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t W, const int64_t *d_edge_index,
+                      const int64_t *d_node_ptr, int64_t G, const GsnPlan *h_plan, int64_t *d_out,
+                      int64_t out_ld, void *d_scratch, size_t scratch_bytes, int32_t *d_status,
+                      void *stream);
+
+/* ------------------------------------------------------------------ */
+/* MP                                                                  */
+/* ------------------------------------------------------------------ */
+
+/* Bytes of workspace for gsn_csr_build. */
+int gsn_csr_workspace_bytes(int64_t N, int64_t E, size_t *bytes);
+
+/*
+ * Groups edge_index columns by d_key[e] (the aggregation index: edge_index[1]
+ * for flow='source_to_target', GSN_sparse.py:125-129) into a CSR:
+ *   d_rowptr int32 [N+1], d_eid int32 [E] (edge_index column ids, ASCENDING
+ *   inside every row -> fixed summation order, deterministic results),
+ *   d_nbr int32 [E] = d_other[d_eid[k]] (the gathered endpoint x_j).
+ * Replaces the COO construction + torch.sparse.sum coalesce of
+ * GSN_sparse.py:140-143.
+ */
+int gsn_csr_build(const int64_t *d_key, const int64_t *d_other, int64_t E, int64_t N, int32_t *d_rowptr,
+                  int32_t *d_eid, int32_t *d_nbr, void *d_ws, size_t ws_bytes, int32_t *d_status,
+                  void *stream);
+
+/*
+ * One column segment of the concatenated 'gin' message / self term.
+ *   neighbour part: src[index(e) * src_ld + c]   index = d_nbr (mode 1), d_eid (mode 2), none (mode 0)
+ *   self part     : self[i * self_ld + c]  (self_ld = 0 broadcasts one row; NULL = 0)  + self_const
+ * Segments express cat(x_j, identifiers, edge_features) as well as the extra
+ * "self-loop" column / embedding of central_encoder (utils_graph_learning.py:211-260)
+ * without materialising the [E, d+1] tensors the reference builds.
+ */
+typedef struct GsnSegment {
+    const float *src;
+    const float *self;
+    int32_t width;
+    int32_t src_ld;
+    int32_t self_ld;
+    int32_t index_mode;   /* 0: no neighbour contribution, 1: gather at neighbour, 2: per-edge row */
+    float self_const;
+    int32_t _pad;
+} GsnSegment;
+
+#define GSN_MAX_SEGMENTS 8
+
+/*
+ * Fused gather -> concat -> scatter-add of the 'gin' message kind
+ * (GSN_sparse.py:103-111,160-164; GSN_edge_sparse.py:95-109,155-159;
+ *  MPNN_* with no identifier segment):
+ *   out[i, :] = (1+eps) * cat_s(self_s[i] + self_const_s) + sum_{e in row i} cat_s(src_s[index_s(e)])
+ * h_segs: HOST array of n_segs segments (device pointers inside).  d_eps: device
+ * float (trainable eps) or NULL (= 0).  fp32 row-major.  out is [N, sum widths].
+ */
+int gsn_mp_gin_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N, int64_t E,
+                   const GsnSegment *h_segs, int32_t n_segs, const float *d_eps, float *d_out, void *stream);
+
+/*
+ * 'ogb' message kind (GSN_edge_sparse_ogb.py:75-84,119-126; MPNN_edge_sparse_ogb):
+ *   out[i,:] = (1+eps) * (x[i] + [id[i] if ids are per node])
+ *            + sum_{e in row i} relu(x[nbr(e)] + (id[nbr(e)] | id[e]) + ef[e])
+ * d_id may be NULL (MPNN).  All operands [.,d].
+ */
+int gsn_mp_ogb_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N, int64_t E,
+                   const float *d_x, const float *d_id, int32_t id_per_edge, const float *d_ef, int32_t d,
+                   const float *d_eps, float *d_out, void *stream);
+
+/*
+ * Plain segment sum  out[i,:] = sum_{e in row i} msgs[eid(e), :]   (the
+ * scatter-add of GSN_sparse.py:140-143 applied to already-computed messages;
+ * also the backward of a row gather).  gather=1 reads msgs[nbr(e)] instead
+ * (out[i] = sum of neighbour rows).
+ */
+int gsn_mp_segment_sum(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                       int64_t E, const float *d_msgs, int32_t d, int32_t gather, float *d_out, void *stream);
+
+/*
+ * 'general' message kind with the first Linear of msg_fn split algebraically
+ * (models_misc.py:52-59 applied to cat(x_i, x_j, ids, ef),
+ *  GSN_edge_sparse.py:161-166):
+ *   h_e   = P[i, 0:dh] + P[nbr(e), dh:2dh] + Q[e, :]            (pre-activation of fc[0], bias inside Q or P)
+ *   S[i]  = sum_{e in row i} act(h_e * scale + shift)            (BatchNorm folded into scale/shift; NULL = identity;
+ *                                                                 act: 0 relu, 1 elu, 2 tanh, 3 identity = models_misc.py:5-15)
+ * P is [N, 2*dh] (x_i half | x_j half), Q is [E, dh] or NULL.  The second
+ * Linear is applied by the caller on N rows: sum_e (W2 h + b2) = W2 S + deg b2.
+ * stats != NULL: instead of S, accumulate per-channel sum and sum of squares of
+ * h_e over all edges into d_stats [2, dh] (double) for training-mode BatchNorm.
+ */
+int gsn_mp_general_edge_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                            int64_t E, const float *d_P, const float *d_Q, int32_t dh, const float *d_scale,
+                            const float *d_shift, int32_t act, float *d_S, double *d_stats, void *stream);
+
+/* ------------------------------------------------------------------ */
+/* misc                                                                */
+/* ------------------------------------------------------------------ */
+int gsn_abi_version(void);
+/* Last CUDA error string seen by this thread inside the library (static storage). */
+const char *gsn_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSN_B200_H_ */
