@@ -1,0 +1,444 @@
+"""bench.py -- graphs/s of preprocess (COUNT) + forward (MP) on ZINC-shaped batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--no-sweep]
+
+Workload (BASELINE.json configs[1]): ZINC-shaped synthetic batch of B=128
+molecules; structural identifiers = cycles k<=8, edge scope (GSN-e), non-induced;
+model = GNNSubstructures, README.md:112 recipe with id_scope local
+(GSN_edge_sparse, general, 4 layers, d_out 128, one-hot encoders, sum readout).
+One step = COUNT over the batch + one_hot_unique encode + model forward.
+
+  value     inputs resident in HBM, whole step replayed as one CUDA graph
+  e2e       same step through GSNPipeline with inputs in pinned HOST memory:
+            H2D of the batch and D2H of the predictions inside the timed region
+  roofline  the scatter kernel (general_edge) timed live with CUDA events in an
+            instrumented eager pass over the same steps
+  N > 1     one process per GPU (torchrun), every rank its own batch (weak
+            scaling, no data-path collective), max-over-ranks time
+
+--impl reference times the reference's CPU path for the same step on the host
+cores: the oracle ports (oracle/count_enum.c with OpenMP = graph-tool-equivalent
+all-maps enumeration, oracle/mp_ref.py = the reference's PyTorch layers on CPU);
+/root/reference itself does not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_MAX = 8
+D_OUT = 128
+N_LAYERS = 4
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def model_args(d_id_cols):
+    """post-process_arguments dict (utils.py:94-161) of the README.md:112 ZINC recipe, id_scope local"""
+    L = N_LAYERS
+    return dict(seed=0, model_name='GSN_edge_sparse', readout='sum', dropout_features=[0.0] * (L + 1), bn=[True] * L,
+                final_projection=[False] * L + [True], inject_ids=False, inject_edge_features=True,
+                random_features=False, id_scope='local', d_msg=[D_OUT] * L, d_out=[D_OUT] * L, d_h=[[D_OUT]] * L,
+                aggr='add', flow='source_to_target', msg_kind='general', train_eps=[False] * L, activation_mlp='relu',
+                bn_mlp=True, jk_mlp=True, degree_embedding='one_hot_encoder', degree_as_tag=[False] * L,
+                retain_features=[False] + [True] * (L - 1), multi_embedding_aggr='sum',
+                input_node_encoder='one_hot_encoder', d_out_node_encoder=D_OUT, edge_encoder='one_hot_encoder',
+                d_out_edge_encoder=[D_OUT] * L, id_embedding='one_hot_encoder', d_out_id_embedding=D_OUT,
+                d_out_degree_embedding=D_OUT, extend_dims=True, activation='relu')
+
+
+def model_ctor(d_in_id):
+    return dict(in_features=1, out_features=1, encoder_ids=None, d_in_id=d_in_id, in_edge_features=1,
+                d_in_node_encoder=[28], d_in_edge_encoder=[4], encoder_degrees=None, d_degree=None)
+
+
+def cycle_edge_lists():
+    import networkx as nx
+    return [list(nx.cycle_graph(k).edges) for k in range(3, K_MAX + 1)]
+
+
+class Clocks:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md)"""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thr.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def build_batches(batch_size, n_batches, seed0):
+    from gsn_b200.synthetic import zinc_like_batch
+    return [zinc_like_batch(batch_size, seed=seed0 + i, distinct=4096 if batch_size > 8192 else None)
+            for i in range(n_batches)]
+
+
+def to_tensors(b, pad_to=None, pin=False, device=None):
+    """numpy batch -> tensors (padded to fixed N/E so that one CUDA graph serves every step)"""
+    t = {'edge_index': torch.from_numpy(b['edge_index']), 'node_ptr': torch.from_numpy(b['node_ptr']),
+         'x': torch.from_numpy(b['x']), 'edge_features': torch.from_numpy(b['edge_features']),
+         'batch': torch.from_numpy(b['batch']), 'degrees': torch.from_numpy(b['degrees'])}
+    if pin:
+        t = {k: v.pin_memory() for k, v in t.items()}
+    if device is not None:
+        t = {k: v.to(device) for k, v in t.items()}
+    return t
+
+
+# ======================================================================================
+# our arm
+# ======================================================================================
+def run_ours(args, rank, world, local_rank):
+    from gsn_b200 import _lib, counting, patterns
+    from gsn_b200.network import GNNSubstructures
+    from gsn_b200.pipeline import GSNPipeline, UniqueEncoder
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False      # fp32 parity (1e-5) needs full-precision GEMMs
+    torch.backends.cudnn.allow_tf32 = False
+    _lib.lib()
+
+    B = args.batch
+    els = cycle_edge_lists()
+    sds = patterns.make_subgraph_dicts(els, 'local')
+    # one fixed-shape batch per rank: CUDA graphs need static shapes, so every step re-runs the same shapes
+    # with different CONTENT (a pool of distinct batches padded to common N/E would be equivalent)
+    pool = build_batches(B, 1, seed0=1000 * rank)
+    calib = build_batches(min(2048, max(B, 512)), 1, seed0=77)[0]
+    ids_cal = counting.count_batch(torch.from_numpy(calib['edge_index']).to(dev), torch.from_numpy(calib['node_ptr']),
+                                   sds, False, 'local', max_nodes_per_graph=64)
+    encoder = UniqueEncoder.fit(ids_cal)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = GNNSubstructures(**model_ctor(encoder.d), **model_args(encoder.d)).to(dev).eval()
+    pipe = GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64)
+    b0 = pool[0]
+    N, E, G = int(b0['node_ptr'][-1]), int(b0['edge_index'].shape[1]), B
+    dev_in = to_tensors(b0, device=dev)
+    host_in = to_tensors(b0, pin=True)
+
+    # ---- correctness of the captured step vs the eager step (cheap sanity, not the parity test)
+    with torch.no_grad():
+        ref_out = pipe.step(dev_in).clone()
+    launches0 = _lib.launch_count()
+    pipe.capture(dev_in, warmup=max(3, args.warmup))
+    with torch.no_grad():
+        l0 = _lib.launch_count()
+        pipe.step(dev_in)
+        my_launches_per_step = _lib.launch_count() - l0
+    out = pipe.replay().clone()
+    torch.cuda.synchronize()
+    assert torch.allclose(out, ref_out, atol=1e-5, rtol=1e-5), 'captured step differs from eager step'
+    assert int(pipe.last_status.item()) == 0
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    dist_on = world > 1
+
+    def barrier():
+        if dist_on:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(fn, steps):
+        """K steps, each bracketed by its own event pair with an L2 flush in between (outside the pairs)"""
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs)      # ms
+
+    # ---- value: device-resident inputs, CUDA-graph replay
+    for _ in range(args.warmup):
+        pipe.replay()
+    with Clocks(local_rank) as clk:
+        ms_total = timed_steps(lambda: pipe.replay(), args.steps)
+        # ---- e2e: pinned host inputs -> H2D -> step -> D2H
+        out_host = torch.empty((G, 1), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            pipe.load(host_in)
+            o = pipe.replay()
+            out_host.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(args.warmup):
+            e2e_step()
+        ms_e2e = timed_steps(e2e_step, args.steps)
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    if dist_on:
+        tt = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        ms_total, ms_e2e = float(tt[0]), float(tt[1])
+    ms_per_step = ms_total / args.steps
+    value = world * G / (ms_per_step * 1e-3)
+    e2e_value = world * G / (ms_e2e / args.steps * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---- instrumented eager pass: per-kernel device time with CUDA events on the launching stream
+        def instrumented(tensors, steps):
+            _lib.TIMER = []
+            with torch.no_grad():
+                for _ in range(steps):
+                    flush.zero_()
+                    pipe.step(tensors)
+            torch.cuda.synchronize()
+            agg = {}
+            for tag, e0, e1 in _lib.TIMER:
+                agg.setdefault(tag, []).append(e0.elapsed_time(e1))
+            _lib.TIMER = None
+            return {k: (float(np.mean(v)) * 1e-3, len(v) // steps) for k, v in agg.items()}   # seconds, calls/step
+
+        peak, peak_src = peaks()
+        prof = instrumented(dev_in, max(3, min(args.steps, 10)))
+        dh = D_OUT
+
+        def scatter_bytes(n, e):
+            # general_edge per launch: P [N,2dh] + Q [E,dh] read, S [N,dh] written, CSR (rowptr, eid, nbr)
+            return 4 * 2 * dh * n + 4 * dh * e + 4 * dh * n + 8 * e + 4 * (n + 1) + 8 * dh
+        t_sc = prof['general_edge'][0]
+        roof = {'bound': 'hbm', 'kernel': 'general_edge_kernel<4,false> (gsn_mp_general_edge_fwd)',
+                'achieved': scatter_bytes(N, E) / t_sc / 1e9, 'peak': peak, 'unit': 'GB/s',
+                'frac': scatter_bytes(N, E) / t_sc / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': scatter_bytes(N, E), 'avg_launch_us': t_sc * 1e6,
+                'launches_per_step': prof['general_edge'][1],
+                'how': 'CUDA events around each gsn_mp_general_edge_fwd call in an eager pass over the same steps'}
+        kernels_us = {k: round(v[0] * 1e6, 2) for k, v in prof.items()}
+        sweep = []
+        if not args.no_sweep:
+            for Bs in (4096, 131072):
+                try:
+                    bb = build_batches(Bs, 1, seed0=5)[0]
+                    tens = to_tensors(bb, device=dev)
+                    n_s, e_s = int(bb['node_ptr'][-1]), int(bb['edge_index'].shape[1])
+                    with torch.no_grad():
+                        for _ in range(2):
+                            pipe.step(tens)
+                    torch.cuda.synchronize()
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t1 = torch.cuda.Event(enable_timing=True)
+                    reps = 3
+                    t0.record()
+                    with torch.no_grad():
+                        for _ in range(reps):
+                            pipe.step(tens)
+                    t1.record()
+                    torch.cuda.synchronize()
+                    ms = t0.elapsed_time(t1) / reps
+                    pr = instrumented(tens, 3)
+                    ts = pr['general_edge'][0]
+                    sweep.append({'batch': Bs, 'N': n_s, 'E': e_s, 'graphs_per_s': Bs / (ms * 1e-3),
+                                  'edges_per_s': e_s / (ms * 1e-3), 'ms_per_step': ms,
+                                  'scatter_GBps': scatter_bytes(n_s, e_s) / ts / 1e9,
+                                  'scatter_frac_of_peak': scatter_bytes(n_s, e_s) / ts / 1e9 / peak,
+                                  'count_ms': pr['count_pattern'][0] * 1e3, 'graph_build_ms': pr['graph_build'][0] * 1e3,
+                                  'kernels_us': {k: round(v[0] * 1e6, 1) for k, v in pr.items()}})
+                    del tens
+                    torch.cuda.empty_cache()
+                except Exception as ex:      # the sweep is informative only; never lose the headline line
+                    sweep.append({'batch': Bs, 'error': repr(ex)[:200]})
+        cpu = cpu_baseline(pool[0], sds_oracle(), encoder, model, budget_s=12.0)
+        line = {
+            'metric': 'graphs/sec preprocess+forward (ZINC batch)', 'value': value, 'unit': 'graphs/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64 counts + fp32 forward',
+            'data': 'synthetic',
+            'config': {'workload': f'ZINC-shaped synthetic batch B={B} per GPU (N={N}, E={E}); COUNT cycles k<=8 edge '
+                                   f'scope non-induced + one_hot_unique encode + GNNSubstructures forward '
+                                   f'(GSN_edge_sparse general, id_scope local, {N_LAYERS} layers, d_out {D_OUT})',
+                       'batch_per_gpu': B, 'N': N, 'E': E, 'id_columns': encoder.d, 'l2': 'flushed between steps '
+                       '(256 MiB memset outside the timed event pairs)', 'cuda_graph': True,
+                       'parallelism': f'batch-sharded x{world}, no data-path collective'},
+            'edges_per_s': world * E / (ms_per_step * 1e-3),
+            'e2e': {'value': e2e_value, 'unit': 'graphs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(my_launches_per_step) * args.steps,
+            'gpu_launches_per_step': int(my_launches_per_step),
+            'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep,
+        }
+    return line
+
+
+def sds_oracle():
+    from oracle import count_vf2
+    return count_vf2.make_subgraph_dicts(cycle_edge_lists(), 'local')
+
+
+# ======================================================================================
+# CPU arm: the oracle ports of the reference path, timed on the host cores
+# ======================================================================================
+def cpu_step_fn(batch, sds_o, encoder, model, threads):
+    from oracle import count_c, mp_ref
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    vocab = [v.cpu().numpy() for v in encoder.vocab]
+    args = model_args(encoder.d)
+    args['d_in_id'] = encoder.d
+    args['d_in_node_encoder'], args['d_in_edge_encoder'] = [28], [4]
+    from gsn_b200.graph_filters.base import SparseFilter  # noqa: F401  (layer configs only)
+    cfgs = []
+    for i in range(N_LAYERS):
+        cfgs.append(dict(uses_ids=(i == 0), uses_ef=True, msg_kind='general', id_scope='local',
+                         flow='source_to_target', activation_name='relu', bn=True, degree_as_tag=False,
+                         retain_features=True, edge_embedding='one_hot_encoder', id_embedding='one_hot_encoder',
+                         extend_dims=True))
+    torch.set_num_threads(threads)
+
+    def step():
+        ids = count_c.count_batch(batch['node_ptr'], batch['edge_ptr'], batch['edge_index'], sds_o, False, 1,
+                                  nthreads=threads)
+        enc = np.stack([np.minimum(np.searchsorted(vocab[c], ids[:, c]), len(vocab[c]) - 1) for c in range(ids.shape[1])], 1)
+        data = {'edge_index': torch.from_numpy(batch['edge_index']), 'batch': torch.from_numpy(batch['batch']),
+                'x': torch.from_numpy(batch['x']), 'edge_features': torch.from_numpy(batch['edge_features']),
+                'degrees': torch.from_numpy(batch['degrees']), 'identifiers': torch.from_numpy(enc)}
+        with torch.no_grad():
+            return mp_ref.gnn_substructures_forward(args, sd, data, cfgs)
+    return step
+
+
+def cpu_baseline(batch, sds_o, encoder, model, budget_s):
+    threads = os.cpu_count() or 1
+    step = cpu_step_fn(batch, sds_o, encoder, model, threads)
+    step()
+    t0, n = time.perf_counter(), 0
+    while True:
+        step()
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 200:
+            break
+    dt = (time.perf_counter() - t0) / n
+    G = len(batch['node_ptr']) - 1
+    return {'value': G / dt, 'unit': 'graphs/s', 'cores': threads, 'kind': 'port',
+            'sample': f'{n} repetitions of the same B={G} step (oracle/count_enum.c OpenMP all-maps COUNT + '
+                      f'oracle/mp_ref.py PyTorch-CPU forward), {dt * 1e3:.1f} ms/step'}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle ports) on the host cores"""
+    from gsn_b200.network import GNNSubstructures
+    from gsn_b200.pipeline import UniqueEncoder
+    from oracle import count_c
+    B = args.batch
+    sds_o = sds_oracle()
+    batch = build_batches(B, 1, seed0=0)[0]
+    calib = build_batches(512, 1, seed0=77)[0]
+    ids_cal = count_c.count_batch(calib['node_ptr'], calib['edge_ptr'], calib['edge_index'], sds_o, False, 1)
+    encoder = UniqueEncoder([torch.from_numpy(np.unique(ids_cal[:, c])) for c in range(ids_cal.shape[1])])
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = GNNSubstructures(**model_ctor(encoder.d), **model_args(encoder.d)).eval()
+    threads = os.cpu_count() or 1
+    step = cpu_step_fn(batch, sds_o, encoder, model, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    N, E = int(batch['node_ptr'][-1]), int(batch['edge_index'].shape[1])
+    v = B / dt
+    sample = f'{args.steps} steps of one B={B} batch; COUNT = oracle/count_enum.c (all maps / |Aut|, OpenMP), ' \
+             f'forward = oracle/mp_ref.py (reference layers restated, PyTorch CPU)'
+    return {'impl': 'reference', 'metric': 'graphs/sec preprocess+forward (ZINC batch)', 'value': v,
+            'unit': 'graphs/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'int64 counts + fp32 forward', 'data': 'synthetic',
+            'config': {'workload': f'ZINC-shaped synthetic batch B={B} (N={N}, E={E}); COUNT cycles k<=8 edge scope + '
+                                   f'one_hot_unique encode + GNNSubstructures forward on the host CPU',
+                       'batch_per_gpu': B, 'N': N, 'E': E},
+            'cpu_baseline': {'value': v, 'unit': 'graphs/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': v, 'unit': 'graphs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=128)
+    ap.add_argument('--no-sweep', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        if rank == 0:
+            print(json.dumps(run_reference(args)), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: gsn_b200 has no CPU path (use --impl reference for the CPU arm)')
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    line = run_ours(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

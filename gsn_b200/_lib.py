@@ -28,6 +28,7 @@ _planp = ctypes.POINTER(GsnPlan)
 _SIGNATURES = {
     'gsn_abi_version': (ctypes.c_int, []),
     'gsn_last_cuda_error': (ctypes.c_char_p, []),
+    'gsn_launch_count': (ctypes.c_uint64, []),
     'gsn_graph_workspace_bytes': (ctypes.c_int, [_i64, _i64, _i32, _szp]),
     'gsn_graph_build': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _sz, _vp, _vp]),
     'gsn_count_scratch_bytes': (ctypes.c_int, [_i64, _i64, _planp, _szp]),
@@ -66,6 +67,29 @@ def lib():
             raise RuntimeError('libgsn_b200.so ABI version mismatch; rebuild')
         _lib = L
     return _lib
+
+
+def launch_count() -> int:
+    return int(lib().gsn_launch_count())
+
+
+# optional per-call device timing (bench.py): TIMER = list -> (name, start_event, end_event) appended per call
+TIMER = None
+
+
+def call(tag: str, fname: str, *args):
+    """invoke one C-ABI entry point, raise on a non-zero return; when TIMER is a
+    list, bracket the call with CUDA events on the current stream"""
+    fn = getattr(lib(), fname)
+    if TIMER is None:
+        check(fn(*args), fname)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    TIMER.append((tag, e0, e1))
+    check(rc, fname)
 
 
 def check(rc: int, what: str):

@@ -84,9 +84,9 @@ class BatchedGraph:
         self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(L.gsn_graph_build(_lib.ptr(self.edge_index), self.E, _lib.ptr(self.node_ptr), self.G, self.N,
-                                         self.W, _lib.ptr(self.ws), nbytes.value, _lib.ptr(self.status),
-                                         _lib.stream_ptr()), 'gsn_graph_build')
+            _lib.call('graph_build', 'gsn_graph_build', _lib.ptr(self.edge_index), self.E, _lib.ptr(self.node_ptr),
+                      self.G, self.N, self.W, _lib.ptr(self.ws), nbytes.value, _lib.ptr(self.status),
+                      _lib.stream_ptr())
 
     def count(self, plans: Sequence[GsnPlan], n_cols: int, scope: int, out: Optional[torch.Tensor] = None):
         rows = self.N if scope == 0 else self.E
@@ -102,10 +102,9 @@ class BatchedGraph:
                 if scratch is None or nb.value > scratch_bytes:
                     scratch = torch.empty(nb.value, dtype=torch.uint8, device=dev)
                     scratch_bytes = nb.value
-                _lib.check(L.gsn_count_pattern(_lib.ptr(self.ws), self.N, self.E, self.W, _lib.ptr(self.edge_index),
-                                               _lib.ptr(self.node_ptr), self.G, ctypes.byref(P), _lib.ptr(out),
-                                               n_cols, _lib.ptr(scratch), scratch_bytes, _lib.ptr(self.status),
-                                               _lib.stream_ptr()), 'gsn_count_pattern')
+                _lib.call('count_pattern', 'gsn_count_pattern', _lib.ptr(self.ws), self.N, self.E, self.W,
+                          _lib.ptr(self.edge_index), _lib.ptr(self.node_ptr), self.G, ctypes.byref(P), _lib.ptr(out),
+                          n_cols, _lib.ptr(scratch), scratch_bytes, _lib.ptr(self.status), _lib.stream_ptr())
         return out
 
     def raise_on_status(self):

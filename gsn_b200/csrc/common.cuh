@@ -8,6 +8,8 @@
 namespace gsn {
 
 extern thread_local char g_last_error[256];
+extern unsigned long long g_launches;   // kernels this library has launched (gsn_launch_count)
+#define GSN_BUMP(n) (__atomic_fetch_add(&gsn::g_launches, (unsigned long long)(n), __ATOMIC_RELAXED))
 
 inline int cuda_fail(cudaError_t e, const char *what) {
     snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));

@@ -221,6 +221,7 @@ int launch_count(const CountParams &prm, int64_t chunks, size_t smem, cudaStream
         attr_set = true;
     }
     count_kernel<W><<<(unsigned)chunks, kCountThreads, smem, stream>>>(prm);
+    GSN_BUMP(1);
     GSN_LAUNCH_OK("count_kernel");
     return GSN_OK;
 }
@@ -309,6 +310,7 @@ extern "C" int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t
             (const int32_t *)(ws + L.slot_col), prm.slot_acc, P.n_cols, d_out, out_ld, P.col0);
         k_missing_check<<<(unsigned)ceil_div(2 * E, TB), TB, 0, stream>>>(
             prm.rowptr, N, (const int32_t *)(ws + L.slot_col), prm.slot_acc, P.n_cols, d_status);
+        GSN_BUMP(2);
         GSN_LAUNCH_OK("k_edge_out");
     }
     return GSN_OK;

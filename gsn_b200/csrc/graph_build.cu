@@ -19,6 +19,7 @@
 namespace gsn {
 
 thread_local char g_last_error[256] = "";
+unsigned long long g_launches = 0;
 
 // ------------------------------------------------------------------ scan
 __global__ void scan_block_sums(const int32_t *__restrict__ in, int32_t *__restrict__ sums, int64_t n) {
@@ -101,6 +102,7 @@ int exclusive_scan_i32(const int32_t *d_in, int32_t *d_out, int64_t n, int32_t *
     scan_block_sums<<<(unsigned)nb, 256, 0, stream>>>(d_in, d_tmp, n);
     scan_sums_inplace<<<1, 1024, 0, stream>>>(d_tmp, nb);
     scan_apply<<<(unsigned)nb, 256, 0, stream>>>(d_in, d_out, d_tmp, n);
+    GSN_BUMP(3);
     GSN_LAUNCH_OK("exclusive_scan_i32");
     return GSN_OK;
 }
@@ -233,6 +235,7 @@ extern "C" int gsn_graph_build(const int64_t *d_edge_index, int64_t E, const int
     }
     const int TB = 256;
     k_node_base<<<(unsigned)ceil_div(N, TB), TB, 0, stream>>>(d_node_ptr, G, N, W, nbase, d_status);
+    GSN_BUMP(3 + (E > 0 ? 2 : 0));
     if (E > 0)
         k_set_bits<<<(unsigned)ceil_div(E, TB), TB, 0, stream>>>(src, dst, E, N, W, nbase,
                                                                 (unsigned long long *)adj, d_status);
@@ -249,4 +252,5 @@ extern "C" int gsn_graph_build(const int64_t *d_edge_index, int64_t E, const int
 }
 
 extern "C" int gsn_abi_version(void) { return GSN_ABI_VERSION; }
+extern "C" uint64_t gsn_launch_count(void) { return __atomic_load_n(&gsn::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char *gsn_last_cuda_error(void) { return gsn::g_last_error; }

@@ -347,6 +347,7 @@ extern "C" int gsn_csr_build(const int64_t *d_key, const int64_t *d_other, int64
         k_fill<<<(unsigned)ceil_div(E, TB), TB, 0, stream>>>(d_key, E, N, d_rowptr, cursor, d_eid);
         k_sort_rows<<<(unsigned)ceil_div(N, TB), TB, 0, stream>>>(d_rowptr, N, d_eid, d_other, d_nbr, d_status, N);
     }
+    GSN_BUMP(E > 0 ? 3 : 0);
     GSN_LAUNCH_OK("gsn_csr_build");
     return GSN_OK;
 }
@@ -374,6 +375,7 @@ extern "C" int gsn_mp_gin_fwd(const int32_t *d_rowptr, const int32_t *d_eid, con
     cudaStream_t stream = (cudaStream_t)stream_;
     if (v4) gin_kernel<4><<<(unsigned)ceil_div(N * (off / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
     else gin_kernel<1><<<(unsigned)ceil_div(N * (int64_t)off, kMpThreads), kMpThreads, 0, stream>>>(p);
+    GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_mp_gin_fwd");
     return GSN_OK;
 }
@@ -388,6 +390,7 @@ extern "C" int gsn_mp_ogb_fwd(const int32_t *d_rowptr, const int32_t *d_eid, con
     const bool v4 = d % 4 == 0 && aligned16(d_x) && aligned16(d_id) && aligned16(d_ef) && aligned16(d_out);
     if (v4) ogb_kernel<4><<<(unsigned)ceil_div(N * (d / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
     else ogb_kernel<1><<<(unsigned)ceil_div(N * d, kMpThreads), kMpThreads, 0, stream>>>(p);
+    GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_mp_ogb_fwd");
     return GSN_OK;
 }
@@ -402,6 +405,7 @@ extern "C" int gsn_mp_segment_sum(const int32_t *d_rowptr, const int32_t *d_eid,
     const bool v4 = d % 4 == 0 && aligned16(d_msgs) && aligned16(d_out);
     if (v4) segsum_kernel<4><<<(unsigned)ceil_div(N * (d / 4), kMpThreads), kMpThreads, 0, stream>>>(d_rowptr, idx, N, d_msgs, d, d_out);
     else segsum_kernel<1><<<(unsigned)ceil_div(N * d, kMpThreads), kMpThreads, 0, stream>>>(d_rowptr, idx, N, d_msgs, d, d_out);
+    GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_mp_segment_sum");
     return GSN_OK;
 }
@@ -425,6 +429,7 @@ extern "C" int gsn_mp_general_edge_fwd(const int32_t *d_rowptr, const int32_t *d
         if (v4) general_edge_kernel<4, false><<<grid, kMpThreads, smem, stream>>>(p);
         else general_edge_kernel<1, false><<<grid, kMpThreads, smem, stream>>>(p);
     }
+    GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_mp_general_edge_fwd");
     return GSN_OK;
 }

@@ -65,12 +65,13 @@ class one_hot_encoder(nn.Module):
     def __init__(self, d_in):
         super().__init__()
         self.d_in = d_in
+        off = torch.tensor([0] + [int(d) for d in d_in[:-1]], dtype=torch.int64).cumsum(0)
+        self.register_buffer('_offsets', off.unsqueeze(0), persistent=False)   # not part of the state_dict
 
     def forward(self, tensor):
-        n = tensor.shape[0]
-        out = torch.zeros((n, int(sum(self.d_in))), device=tensor.device)
-        off = torch.as_tensor([0] + list(self.d_in[:-1]), device=tensor.device).cumsum(0)
-        out.scatter_(1, tensor[:, :len(self.d_in)] + off.unsqueeze(0), 1.0)
+        n, c = tensor.shape[0], tensor.shape[1]
+        out = torch.zeros((n, int(sum(self.d_in[:c]))), device=tensor.device)
+        out.scatter_(1, tensor + self._offsets[:, :c].to(tensor.device), 1.0)
         return out
 
     def __repr__(self):

@@ -62,9 +62,7 @@ class EdgePlan:
         ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
         key, other = ei[select], ei[1 - select]
         with torch.cuda.device(dev):
-            _lib.check(L.gsn_csr_build(_lib.ptr(key), _lib.ptr(other), self.E, self.N, _lib.ptr(self.rowptr),
-                                       _lib.ptr(self.eid), _lib.ptr(self.nbr), _lib.ptr(ws), nb.value,
-                                       _lib.ptr(self.status), _lib.stream_ptr()), 'gsn_csr_build')
+            _lib.call('csr_build', 'gsn_csr_build', _lib.ptr(key), _lib.ptr(other), self.E, self.N, _lib.ptr(self.rowptr), _lib.ptr(self.eid), _lib.ptr(self.nbr), _lib.ptr(ws), nb.value, _lib.ptr(self.status), _lib.stream_ptr())
         self._ws = ws           # keep alive until the stream has consumed it
         self._transposed: Optional['EdgePlan'] = None
         self._deg: Optional[torch.Tensor] = None
@@ -145,9 +143,7 @@ def gin_aggregate(plan: EdgePlan, segments: Sequence[dict], eps: Optional[torch.
     out = torch.empty((plan.N, D), dtype=torch.float32, device=plan.device)
     eps_t = _f32c(eps, 'eps')
     with torch.cuda.device(plan.device):
-        _lib.check(_lib.lib().gsn_mp_gin_fwd(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N,
-                                             plan.E, ctypes.cast(segs, ctypes.c_void_p), len(segments),
-                                             _lib.ptr(eps_t), _lib.ptr(out), _lib.stream_ptr()), 'gsn_mp_gin_fwd')
+        _lib.call('mp_gin', 'gsn_mp_gin_fwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N, plan.E, ctypes.cast(segs, ctypes.c_void_p), len(segments), _lib.ptr(eps_t), _lib.ptr(out), _lib.stream_ptr())
     return out
 
 
@@ -163,9 +159,7 @@ def ogb_aggregate(plan: EdgePlan, x: torch.Tensor, identifiers: Optional[torch.T
     out = torch.empty((plan.N, d), dtype=torch.float32, device=plan.device)
     eps_t = _f32c(eps, 'eps')
     with torch.cuda.device(plan.device):
-        _lib.check(_lib.lib().gsn_mp_ogb_fwd(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N,
-                                             plan.E, _lib.ptr(x), _lib.ptr(idt), int(bool(id_per_edge)), _lib.ptr(ef),
-                                             d, _lib.ptr(eps_t), _lib.ptr(out), _lib.stream_ptr()), 'gsn_mp_ogb_fwd')
+        _lib.call('mp_ogb', 'gsn_mp_ogb_fwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N, plan.E, _lib.ptr(x), _lib.ptr(idt), int(bool(id_per_edge)), _lib.ptr(ef), d, _lib.ptr(eps_t), _lib.ptr(out), _lib.stream_ptr())
     return out
 
 
@@ -175,9 +169,7 @@ def segment_sum(plan: EdgePlan, rows: torch.Tensor, gather_neighbour: bool = Fal
     d = rows.shape[1]
     out = torch.empty((plan.N, d), dtype=torch.float32, device=plan.device)
     with torch.cuda.device(plan.device):
-        _lib.check(_lib.lib().gsn_mp_segment_sum(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr),
-                                                 plan.N, plan.E, _lib.ptr(rows), d, int(bool(gather_neighbour)),
-                                                 _lib.ptr(out), _lib.stream_ptr()), 'gsn_mp_segment_sum')
+        _lib.call('segment_sum', 'gsn_mp_segment_sum', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N, plan.E, _lib.ptr(rows), d, int(bool(gather_neighbour)), _lib.ptr(out), _lib.stream_ptr())
     return out
 
 
@@ -192,11 +184,7 @@ def general_edge(plan: EdgePlan, P: torch.Tensor, Q: Optional[torch.Tensor], sca
     dh = P.shape[1] // 2
     S = torch.empty((plan.N, dh), dtype=torch.float32, device=plan.device)
     with torch.cuda.device(plan.device):
-        _lib.check(_lib.lib().gsn_mp_general_edge_fwd(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr),
-                                                      plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), dh,
-                                                      _lib.ptr(_f32c(scale, 'scale')), _lib.ptr(_f32c(shift, 'shift')),
-                                                      ACTIVATIONS[activation], _lib.ptr(S), None,
-                                                      _lib.stream_ptr()), 'gsn_mp_general_edge_fwd')
+        _lib.call('general_edge', 'gsn_mp_general_edge_fwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), dh, _lib.ptr(_f32c(scale, 'scale')), _lib.ptr(_f32c(shift, 'shift')), ACTIVATIONS[activation], _lib.ptr(S), None, _lib.stream_ptr())
     return S
 
 
@@ -209,8 +197,5 @@ def general_edge_stats(plan: EdgePlan, P: torch.Tensor, Q: Optional[torch.Tensor
     dh = P.shape[1] // 2
     stats = torch.zeros((2, dh), dtype=torch.float64, device=plan.device)
     with torch.cuda.device(plan.device):
-        _lib.check(_lib.lib().gsn_mp_general_edge_fwd(_lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr),
-                                                      plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), dh, None, None, 3,
-                                                      None, _lib.ptr(stats), _lib.stream_ptr()),
-                   'gsn_mp_general_edge_fwd')
+        _lib.call('general_edge_stats', 'gsn_mp_general_edge_fwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), dh, None, None, 3, None, _lib.ptr(stats), _lib.stream_ptr())
     return stats

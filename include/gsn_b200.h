@@ -215,6 +215,8 @@ int gsn_mp_general_edge_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const
 /* misc                                                                */
 /* ------------------------------------------------------------------ */
 int gsn_abi_version(void);
+/* Number of CUDA kernels this library has launched (or recorded into a capturing stream) so far. */
+uint64_t gsn_launch_count(void);
 /* Last CUDA error string seen by this thread inside the library (static storage). */
 const char *gsn_last_cuda_error(void);
 
