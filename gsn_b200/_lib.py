@@ -39,6 +39,10 @@ _SIGNATURES = {
     'gsn_mp_ogb_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     'gsn_mp_segment_sum': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp]),
     'gsn_mp_general_edge_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    'gsn_mp_general_edge_idx_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
+    'gsn_linear_fwd': (ctypes.c_int, [_vp, _vp]),
+    'gsn_pool_ptr': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    'gsn_encode_rows': (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

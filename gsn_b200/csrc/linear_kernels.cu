@@ -1,0 +1,224 @@
+// Dense tail of the layers: fused Linear (+ second input block + rank-1 term +
+// embedding-table term) -> per-channel affine (BatchNorm eval) -> activation.
+//
+// Replaces, per call, the chain  torch.cat -> nn.Linear -> BatchNorm1d -> act  of
+// /root/reference/models_misc.py:52-59 as used for update_fn
+// (graph_filters/GSN_edge_sparse.py:111-115) and for the N-row halves of the split
+// msg_fn (see mp_kernels.cu):
+//
+//   C[m,n] = act( ( sum_k A1[m,k] W[n,k] + sum_k A2[m,k] W[n,K1+k]
+//                   + row_scale[m] * row_vec[n] + tab[tab_idx[m], n] + bias[n] ) * scale[n] + shift[n] )
+//
+// W is in nn.Linear layout [Nout, K1+K2] (K contiguous), so both operands are
+// K-major.  fp32 FFMA accumulation (plain TF32 cannot meet the 1e-5 parity bar);
+// 64x64 or 128x128 CTA tiles, BK = 16, register double-buffering of the global
+// loads, transposed shared tiles (conflict-free 128-bit reads).
+#include "common.cuh"
+
+namespace gsn {
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    switch (act) {
+        case 0: return fmaxf(v, 0.0f);
+        case 1: return v > 0.0f ? v : expm1f(v);
+        case 2: return tanhf(v);
+        default: return v;
+    }
+}
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) linear_kernel(const __grid_constant__ GsnLinear p) {
+    constexpr int BK = 16;
+    constexpr int THREADS = (BM / TM) * (BN / TN);
+    constexpr int A_LOADS = BM * BK / 4 / THREADS;   // float4 loads per thread per tile
+    constexpr int B_LOADS = BN * BK / 4 / THREADS;
+    static_assert(A_LOADS >= 1 && B_LOADS >= 1, "tile too small for the thread count");
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int K = p.K1 + p.K2;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+    // one float4 (4 consecutive k) of row r of the logical A = [A1 | A2] / of W
+    auto load_a = [&](int r, int k) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int m = m0 + r;
+        if (m >= p.M || k >= K) return v;
+        float t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int kk = k + i;
+            float x = 0.f;
+            if (kk < p.K1) x = __ldg(p.A1 + (int64_t)m * p.lda1 + kk);
+            else if (kk < K) x = __ldg(p.A2 + (int64_t)m * p.lda2 + (kk - p.K1));
+            t[i] = x;
+        }
+        return make_float4(t[0], t[1], t[2], t[3]);
+    };
+    auto load_a_vec = [&](int r, int k) -> float4 {
+        const int m = m0 + r;
+        if (m >= p.M || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < p.K1) return __ldg(reinterpret_cast<const float4 *>(p.A1 + (int64_t)m * p.lda1 + k));
+        return __ldg(reinterpret_cast<const float4 *>(p.A2 + (int64_t)m * p.lda2 + (k - p.K1)));
+    };
+    auto load_b = [&](int r, int k) -> float4 {
+        const int n = n0 + r;
+        if (n >= p.Nout || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.vec_ok) return __ldg(reinterpret_cast<const float4 *>(p.W + (int64_t)n * p.ldw + k));
+        float t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = (k + i < K) ? __ldg(p.W + (int64_t)n * p.ldw + k + i) : 0.f;
+        return make_float4(t[0], t[1], t[2], t[3]);
+    };
+
+    float4 ra[A_LOADS], rb[B_LOADS];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < A_LOADS; ++i) {
+            const int l = tid + i * THREADS;          // float4 id inside the tile
+            const int r = l / (BK / 4), kq = (l % (BK / 4)) * 4;
+            ra[i] = p.vec_ok ? load_a_vec(r, k0 + kq) : load_a(r, k0 + kq);
+        }
+#pragma unroll
+        for (int i = 0; i < B_LOADS; ++i) {
+            const int l = tid + i * THREADS;
+            const int r = l / (BK / 4), kq = (l % (BK / 4)) * 4;
+            rb[i] = load_b(r, k0 + kq);
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_LOADS; ++i) {
+            const int l = tid + i * THREADS;
+            const int r = l / (BK / 4), kq = (l % (BK / 4)) * 4;
+            As[buf][kq + 0][r] = ra[i].x; As[buf][kq + 1][r] = ra[i].y;
+            As[buf][kq + 2][r] = ra[i].z; As[buf][kq + 3][r] = ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < B_LOADS; ++i) {
+            const int l = tid + i * THREADS;
+            const int r = l / (BK / 4), kq = (l % (BK / 4)) * 4;
+            Bs[buf][kq + 0][r] = rb[i].x; Bs[buf][kq + 1][r] = rb[i].y;
+            Bs[buf][kq + 2][r] = rb[i].z; Bs[buf][kq + 3][r] = rb[i].w;
+        }
+    };
+
+    const int nk = (K + BK - 1) / BK;
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) fetch((kt + 1) * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                float4 v = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * TM + i]);
+                a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+                float4 v = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * TN + j]);
+                b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            stash(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= p.M) continue;
+        const float rs = p.row_scale ? __ldg(p.row_scale + m) : 0.f;
+        const float *trow = p.tab ? p.tab + (int64_t)__ldg(p.tab_idx + m) * p.tab_ld : nullptr;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= p.Nout) continue;
+            float v = acc[i][j];
+            if (p.row_vec) v = fmaf(rs, __ldg(p.row_vec + n), v);
+            if (trow) v += __ldg(trow + n);
+            if (p.bias) v += __ldg(p.bias + n);
+            if (p.scale) v = fmaf(v, __ldg(p.scale + n), p.shift ? __ldg(p.shift + n) : 0.f);
+            else if (p.shift) v += __ldg(p.shift + n);
+            v = act_apply(v, p.act);
+            float *dst = p.C + (int64_t)m * p.ldc + n;
+            *dst = p.accumulate ? *dst + v : v;
+        }
+    }
+}
+
+// rows of x summed per contiguous segment [ptr[g], ptr[g+1])  (readout of a PyG batch:
+// global_add_pool_sparse / global_mean_pool_sparse, utils_graph_learning.py:23-41)
+__global__ void pool_ptr_kernel(const float *__restrict__ x, const int64_t *__restrict__ ptr, int64_t G, int d, int ldx,
+                                int mean, float *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * d) return;
+    const int64_t g = t / d;
+    const int c = (int)(t % d);
+    const int64_t r0 = ptr[g], r1 = ptr[g + 1];
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += __ldg(x + r * ldx + c);
+    if (mean) acc /= (r1 > r0 ? (float)(r1 - r0) : 1.0f);
+    out[g * d + c] = acc;
+}
+
+}  // namespace gsn
+
+using namespace gsn;
+
+extern "C" int gsn_linear_fwd(const GsnLinear *h_p, void *stream_) {
+    if (!h_p) return GSN_E_INVALID;
+    GsnLinear p = *h_p;
+    if (p.M < 0 || p.Nout < 1 || p.K1 < 0 || p.K2 < 0 || p.K1 + p.K2 < 0 || !p.C) return GSN_E_INVALID;
+    if ((p.K1 > 0 && !p.A1) || (p.K2 > 0 && !p.A2) || (p.K1 + p.K2 > 0 && !p.W)) return GSN_E_INVALID;
+    if ((p.row_scale == nullptr) != (p.row_vec == nullptr)) return GSN_E_INVALID;
+    if ((p.tab == nullptr) != (p.tab_idx == nullptr)) return GSN_E_INVALID;
+    if (p.M == 0) return GSN_OK;
+    auto al16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+    p.vec_ok = (p.K1 % 4 == 0 && p.K2 % 4 == 0 && p.lda1 % 4 == 0 && (p.K2 == 0 || p.lda2 % 4 == 0) && p.ldw % 4 == 0 &&
+                al16(p.A1) && al16(p.A2) && al16(p.W)) ? 1 : 0;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t tiles64 = ceil_div(p.M, 64) * ceil_div(p.Nout, 64);
+    if (tiles64 >= 4 * kNumSMs && p.Nout >= 96) {
+        dim3 grid((unsigned)ceil_div(p.Nout, 128), (unsigned)ceil_div(p.M, 128));
+        linear_kernel<128, 128, 8, 8><<<grid, 256, 0, stream>>>(p);
+    } else if (tiles64 >= kNumSMs / 2) {
+        dim3 grid((unsigned)ceil_div(p.Nout, 64), (unsigned)ceil_div(p.M, 64));
+        linear_kernel<64, 64, 4, 4><<<grid, 256, 0, stream>>>(p);
+    } else {
+        dim3 grid((unsigned)ceil_div(p.Nout, 64), (unsigned)ceil_div(p.M, 16));
+        linear_kernel<16, 64, 4, 4><<<grid, 64, 0, stream>>>(p);
+    }
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_linear_fwd");
+    return GSN_OK;
+}
+
+extern "C" int gsn_pool_ptr(const float *d_x, const int64_t *d_ptr, int64_t G, int32_t d, int32_t ldx, int32_t mean,
+                            float *d_out, void *stream_) {
+    if (G < 0 || d < 1 || !d_ptr || !d_out || (G > 0 && !d_x)) return GSN_E_INVALID;
+    if (G == 0) return GSN_OK;
+    pool_ptr_kernel<<<(unsigned)ceil_div(G * d, 256), 256, 0, (cudaStream_t)stream_>>>(d_x, d_ptr, G, d, ldx, mean, d_out);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_pool_ptr");
+    return GSN_OK;
+}

@@ -312,6 +312,108 @@ __global__ void __launch_bounds__(kMpThreads) general_edge_kernel(const __grid_c
     }
 }
 
+// ------------------------------------------------------------------ index fast path
+struct GenIdxParams {
+    const int32_t *rowptr, *eid, *nbr;
+    int64_t N;
+    const float *P, *Q, *Tn, *Te, *scale, *shift;
+    const int32_t *node_rows, *edge_rows;
+    int n_node_cols, n_edge_cols, dh, act;
+    float *S;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kMpThreads) general_edge_idx_kernel(const __grid_constant__ GenIdxParams p) {
+    const int dh = p.dh;
+    const int cpr = dh / VEC;
+    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t row = t / cpr;
+    const int c = (int)(t % cpr) * VEC;
+    float base[VEC], sc[VEC], sf[VEC], acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        base[i] = 0.f;
+        sc[i] = p.scale ? __ldg(p.scale + c + i) : 1.0f;
+        sf[i] = p.shift ? __ldg(p.shift + c + i) : 0.0f;
+        acc[i] = 0.f;
+    }
+    if (p.P) {
+        Vec<VEC> v = Vec<VEC>::ld(p.P + row * (2 * dh) + c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) base[i] += v.v[i];
+    }
+    for (int q = 0; q < p.n_node_cols; ++q) {
+        Vec<VEC> v = Vec<VEC>::ld(p.Tn + (int64_t)__ldg(p.node_rows + row * p.n_node_cols + q) * (2 * dh) + c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) base[i] += v.v[i];
+    }
+    const int kend = p.rowptr[row + 1];
+    for (int k = p.rowptr[row]; k < kend; ++k) {
+        const int j = __ldg(p.nbr + k), e = __ldg(p.eid + k);
+        float h[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) h[i] = base[i];
+        if (p.P) {
+            Vec<VEC> v = Vec<VEC>::ld(p.P + (int64_t)j * (2 * dh) + dh + c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) h[i] += v.v[i];
+        }
+        for (int q = 0; q < p.n_node_cols; ++q) {
+            Vec<VEC> v = Vec<VEC>::ld(p.Tn + (int64_t)__ldg(p.node_rows + (int64_t)j * p.n_node_cols + q) * (2 * dh) + dh + c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) h[i] += v.v[i];
+        }
+        if (p.Q) {
+            Vec<VEC> v = Vec<VEC>::ld(p.Q + (int64_t)e * dh + c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) h[i] += v.v[i];
+        }
+        for (int q = 0; q < p.n_edge_cols; ++q) {
+            Vec<VEC> v = Vec<VEC>::ld(p.Te + (int64_t)__ldg(p.edge_rows + (int64_t)e * p.n_edge_cols + q) * dh + c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) h[i] += v.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += apply_act(fmaf(h[i], sc[i], sf[i]), p.act);
+    }
+    Vec<VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+    o.st(p.S + row * dh + c);
+}
+
+struct EncodeParams {
+    GsnEncodeCol col[GSN_MAX_ENCODE_COLS];
+    int n_cols;
+    const int64_t *vocab;
+    int64_t R;
+    int32_t *out;
+};
+
+__global__ void encode_rows_kernel(const __grid_constant__ EncodeParams p) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.R * p.n_cols) return;
+    const int64_t r = t / p.n_cols;
+    const int c = (int)(t % p.n_cols);
+    const GsnEncodeCol &col = p.col[c];
+    const int64_t v = __ldg(col.src + r * col.stride);
+    int rank;
+    if (col.vocab_end > col.vocab_begin) {
+        int lo = col.vocab_begin, hi = col.vocab_end;     // first entry >= v  (torch.bucketize / np.unique inverse)
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(p.vocab + mid) < v) lo = mid + 1; else hi = mid;
+        }
+        rank = lo - col.vocab_begin;
+        const int last = col.vocab_end - col.vocab_begin - 1;
+        if (rank > last) rank = last;
+    } else {
+        rank = (int)v;
+    }
+    p.out[t] = col.table_off + rank;
+}
+
 inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace gsn
@@ -431,5 +533,42 @@ extern "C" int gsn_mp_general_edge_fwd(const int32_t *d_rowptr, const int32_t *d
     }
     GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_mp_general_edge_fwd");
+    return GSN_OK;
+}
+
+extern "C" int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d_vocab, int64_t R,
+                               int32_t *d_out, void *stream_) {
+    if (!h_cols || n_cols < 1 || n_cols > GSN_MAX_ENCODE_COLS || R < 0 || !d_out) return GSN_E_INVALID;
+    if (R == 0) return GSN_OK;
+    EncodeParams p;
+    for (int i = 0; i < n_cols; ++i) {
+        if (!h_cols[i].src) return GSN_E_INVALID;
+        if (h_cols[i].vocab_end > h_cols[i].vocab_begin && !d_vocab) return GSN_E_INVALID;
+        p.col[i] = h_cols[i];
+    }
+    p.n_cols = n_cols; p.vocab = d_vocab; p.R = R; p.out = d_out;
+    encode_rows_kernel<<<(unsigned)ceil_div(R * n_cols, 256), 256, 0, (cudaStream_t)stream_>>>(p);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_encode_rows");
+    return GSN_OK;
+}
+
+extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr,
+                                           int64_t N, int64_t E, const float *d_P, const float *d_Q,
+                                           const int32_t *d_node_rows, int32_t n_node_cols, const float *d_Tn,
+                                           const int32_t *d_edge_rows, int32_t n_edge_cols, const float *d_Te,
+                                           int32_t dh, const float *d_scale, const float *d_shift, int32_t act,
+                                           float *d_S, void *stream_) {
+    if (N < 0 || E < 0 || dh < 1 || !d_rowptr || !d_S || n_node_cols < 0 || n_edge_cols < 0) return GSN_E_INVALID;
+    if ((n_node_cols > 0 && (!d_node_rows || !d_Tn)) || (n_edge_cols > 0 && (!d_edge_rows || !d_Te))) return GSN_E_INVALID;
+    if (N == 0) return GSN_OK;
+    GenIdxParams p{d_rowptr, d_eid, d_nbr, N, d_P, d_Q, d_Tn, d_Te, d_scale, d_shift, d_node_rows, d_edge_rows,
+                   n_node_cols, n_edge_cols, dh, act, d_S};
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool v4 = dh % 4 == 0 && aligned16(d_P) && aligned16(d_Q) && aligned16(d_S) && aligned16(d_Tn) && aligned16(d_Te);
+    if (v4) general_edge_idx_kernel<4><<<(unsigned)ceil_div(N * (dh / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
+    else general_edge_idx_kernel<1><<<(unsigned)ceil_div(N * (int64_t)dh, kMpThreads), kMpThreads, 0, stream>>>(p);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");
     return GSN_OK;
 }

@@ -224,7 +224,7 @@ def _segment_rows(x, batch, num_graphs=None):
         _pool_plans.append((key, plan))
         if len(_pool_plans) > 8:
             _pool_plans.pop(0)
-    return ops.segment_sum(plan, x), plan
+    return ops.segment_sum_ad(plan, x.float()), plan
 
 
 def global_add_pool_sparse(x, batch, num_graphs=None):

@@ -1,0 +1,243 @@
+"""Fused inference forward of GNNSubstructures ('general' message kind).
+
+Same arithmetic as /root/reference/models_graph_classification.py:204-247 in eval
+mode, re-associated so that the whole forward is a handful of library kernels:
+
+  * categorical inputs stay indices: a one-hot block times a weight matrix is a
+    table row (one_hot_encoder, utils_graph_learning.py:170-187, followed by the
+    first Linear of msg_fn / update_fn), and one_hot_unique
+    (utils_encoding.py:37-59) is a binary search over the sorted vocabulary, so
+    raw identifier counts go straight from COUNT into the message kernel;
+  * BatchNorm1d (eval) is a per-channel scale/shift applied in the kernels'
+    epilogues; the second Linear of msg_fn commutes with the neighbour sum and is
+    pre-multiplied into update_fn's first Linear:
+        cat(x, sum_e(W2 h_e + b2)) U1^T = x U1x^T + S (U1a W2)^T + deg (U1a b2)
+  * per layer: [P GEMM] -> message kernel -> update GEMM -> output GEMM (+ model BN + act).
+
+Only inference (no autograd); training and every other configuration use the
+per-layer path in graph_filters/.  Parity: tests/test_fused_gpu.py.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .encoders import one_hot_encoder
+
+
+def _is_onehot(enc) -> bool:
+    return enc.encoder_name == 'one_hot_encoder'
+
+
+def supported(model) -> bool:
+    from .network import GNNSubstructures
+    if not isinstance(model, GNNSubstructures) or model.random_features:
+        return False
+    ok_enc = lambda e: e.encoder_name in ('one_hot_encoder', 'None')
+    if not ok_enc(model.input_node_encoder) or not all(ok_enc(e) for e in model.edge_encoder):
+        return False
+    if not all(_is_onehot(e) for e in model.id_encoder):
+        return False
+    for conv in model.conv:
+        if conv.msg_kind != 'general' or conv.degree_as_tag or conv.aggr != 'add' or conv.msg_fn.depth != 2 \
+                or conv.update_fn.depth != 2:
+            return False
+    if model.final_projection[0] and _is_onehot(model.input_node_encoder):
+        return False
+    return True
+
+
+class FusedForward:
+
+    def __init__(self, model):
+        if not supported(model):
+            raise NotImplementedError('fused forward: unsupported model configuration')
+        self.model = model
+        self._stamp = None
+        self.layers: List[dict] = []
+
+    # ------------------------------------------------------------------ weight preparation
+    def _version_stamp(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.model.parameters()) + list(self.model.buffers()))
+
+    @torch.no_grad()
+    def prepare(self):
+        m = self.model
+        self.layers = []
+        x_cat = _is_onehot(m.input_node_encoder)
+        for i, conv in enumerate(m.conv):
+            f, u = conv.msg_fn, conv.update_fn
+            dh = f.fc[0].weight.shape[0]
+            d_in = conv._dims[0]
+            ee = m.edge_encoder[i if m.inject_edge_features else 0] if conv.uses_ef else None
+            ie = m.id_encoder[i if m.inject_ids else 0] if conv.uses_ids else None
+            ef_cat = ee is not None and _is_onehot(ee)
+            d_id = ie.d_out if ie is not None else 0
+            d_ef = ee.d_out if ee is not None else 0
+            Wxi, Wxj, Wii, Wij, Wq_id, Wq_ef = conv._split_first_linear(d_in, d_id, d_ef)
+            L = {'dh': dh, 'act_mlp': conv.activation_name, 'x_cat': x_cat and i == 0, 'ef_cat': ef_cat,
+                 'uses_ids': conv.uses_ids, 'uses_ef': conv.uses_ef, 'local': conv.id_scope == 'local', 'flow': conv.flow}
+            # node side of the first Linear
+            Wp = torch.cat((Wxi, Wxj), 0).contiguous()                  # [2dh, d_in]
+            node_tables = []
+            if L['x_cat']:
+                node_tables.append(Wp.t().contiguous())                  # [d_in rows, 2dh]
+                L['Wp'] = None
+            else:
+                L['Wp'] = Wp
+            if conv.uses_ids and not L['local']:
+                node_tables.append(torch.cat((Wii, Wij), 0).t().contiguous())   # [d_id rows, 2dh]
+            L['Tn'] = torch.cat(node_tables, 0).contiguous() if node_tables else None
+            L['Tn_off_ids'] = node_tables[0].shape[0] if (L['x_cat'] and len(node_tables) == 2) else 0
+            # edge side
+            edge_tables = []
+            if conv.uses_ids and L['local']:
+                edge_tables.append(Wq_id.t().contiguous())               # [d_id rows, dh]
+            L['Te_off_ef'] = edge_tables[0].shape[0] if edge_tables else 0
+            if conv.uses_ef:
+                if ef_cat:
+                    edge_tables.append(Wq_ef.t().contiguous())
+                    L['Wq_ef'] = None
+                else:
+                    L['Wq_ef'] = Wq_ef.contiguous()
+            L['Te'] = torch.cat(edge_tables, 0).contiguous() if edge_tables else None
+            # BatchNorm of msg_fn + bias of its first Linear -> scale / shift
+            s0, t0 = f.bn_affine(0)
+            b1 = f.fc[0].bias
+            if s0 is None:
+                L['scale'], L['shift'] = None, b1.clone()
+            else:
+                L['scale'], L['shift'] = s0.contiguous(), (b1 * s0 + t0).contiguous()
+            # update_fn with the second message Linear folded in
+            W2, b2 = f.fc[1].weight, f.fc[1].bias
+            U1, c1 = u.fc[0].weight, u.fc[0].bias
+            U1x, U1a = U1[:, :d_in], U1[:, d_in:]
+            Wf = (U1a.double() @ W2.double()).float()                     # [dh_u, dh]
+            L['vf'] = (U1a.double() @ b2.double()).float().contiguous()
+            if L['x_cat']:
+                L['Wu'] = Wf.contiguous()
+                L['Tu'] = U1x.t().contiguous()                            # [d_in rows, dh_u]
+            else:
+                L['Wu'] = torch.cat((U1x, Wf), 1).contiguous()            # [dh_u, d_in + dh]
+                L['Tu'] = None
+            L['c1'] = c1.contiguous()
+            su, tu = u.bn_affine(0)
+            L['su'], L['tu'] = (None, None) if su is None else (su.contiguous(), tu.contiguous())
+            L['U2'], L['c2'] = u.fc[1].weight.contiguous(), u.fc[1].bias.contiguous()
+            if m.bn[i]:
+                bn = m.batch_norms[i]
+                inv = torch.rsqrt(bn.running_var + bn.eps)
+                sm = bn.weight * inv
+                L['sm'], L['tm'] = sm.contiguous(), (bn.bias - bn.running_mean * sm).contiguous()
+            else:
+                L['sm'], L['tm'] = None, None
+            self.layers.append(L)
+        self._act_model = {torch.nn.ReLU: 'relu', torch.nn.ELU: 'elu', torch.nn.Tanh: 'tanh'}.get(type(m.activation), 'identity')
+        # JK projections
+        self.proj = []
+        for i, pr in enumerate(m.lin_proj):
+            if not m.final_projection[i]:
+                self.proj.append(None)
+            elif isinstance(pr, torch.nn.Linear):
+                self.proj.append(('linear', pr.weight.contiguous(), pr.bias.contiguous()))
+            else:
+                if pr.depth != 2:
+                    raise NotImplementedError('JK mlp depth != 2')
+                s, t = pr.bn_affine(0)
+                self.proj.append(('mlp', pr.fc[0].weight.contiguous(), pr.fc[0].bias.contiguous(),
+                                  None if s is None else s.contiguous(), None if t is None else t.contiguous(),
+                                  pr.fc[1].weight.contiguous(), pr.fc[1].bias.contiguous(), pr.activation_name))
+        self._stamp = self._version_stamp()
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def __call__(self, data, raw_identifiers: Optional[torch.Tensor] = None, vocab: Optional[List[torch.Tensor]] = None):
+        """data: same attribute bag as GNNSubstructures.forward plus `node_ptr` (int64 [G+1]).
+        raw_identifiers/vocab: un-encoded COUNT output and the one_hot_unique vocabulary; when omitted,
+        data.identifiers must hold the encoded ranks (as in the reference)."""
+        m = self.model
+        if m.training:
+            raise RuntimeError('FusedForward is inference-only')
+        if self._stamp != self._version_stamp():
+            self.prepare()
+        dev = data.edge_index.device
+        edge_index = data.edge_index
+        N = data.x.shape[0]
+        E = edge_index.shape[1]
+        node_ptr = data.node_ptr
+
+        # identifier rows into the one-hot table of the id encoder (offset inside the table added later)
+        ids = raw_identifiers if raw_identifiers is not None else data.identifiers
+        id_dims = m.id_encoder[0].encoder.d_in
+        id_off, o = [], 0
+        for d in id_dims:
+            id_off.append(o)
+            o += int(d)
+        if vocab is not None:
+            vcat = torch.cat(vocab)
+            vptr, o2 = [], 0
+            for v in vocab:
+                vptr.append((o2, o2 + v.numel()))
+                o2 += v.numel()
+        else:
+            vcat, vptr = None, [None] * len(id_dims)
+
+        x = None
+        x_cat = _is_onehot(m.input_node_encoder)
+        xi = data.x if data.x.dim() == 2 else data.x.unsqueeze(-1)
+        if not x_cat:
+            x = m.input_node_encoder(data.x)
+        x_interm = [x]
+        for i, (conv, L) in enumerate(zip(m.conv, self.layers)):
+            plan = ops.edge_plan(edge_index, N, L['flow'])
+            dh = L['dh']
+            # ---- index columns
+            node_cols, edge_cols = [], []
+            if L['x_cat']:
+                node_cols.append((xi[:, 0], None, 0))
+            if L['uses_ids']:
+                cols = [(ids[:, c], vptr[c], id_off[c]) for c in range(ids.shape[1])]
+                if L['local']:
+                    edge_cols += cols
+                else:
+                    node_cols += [(s, v, off + L['Tn_off_ids']) for s, v, off in cols]
+            if L['uses_ef'] and L['ef_cat']:
+                efi = data.edge_features if data.edge_features.dim() == 2 else data.edge_features.unsqueeze(-1)
+                edge_cols.append((efi[:, 0], None, L['Te_off_ef']))
+            node_rows = ops.encode_rows(node_cols, vcat, N, dev) if node_cols else None
+            edge_rows = ops.encode_rows(edge_cols, vcat, E, dev) if edge_cols else None
+            # ---- dense parts
+            P = ops.linear(x, L['Wp']) if L['Wp'] is not None else None
+            Q = None
+            if L['uses_ef'] and not L['ef_cat']:
+                ee = m.edge_encoder[i if m.inject_edge_features else 0]
+                Q = ops.linear(ee(data.edge_features).contiguous(), L['Wq_ef'])
+            S = ops.general_edge_idx(plan, dh, P=P, Q=Q, node_rows=node_rows, Tn=L['Tn'], edge_rows=edge_rows,
+                                     Te=L['Te'], scale=L['scale'], shift=L['shift'], activation=L['act_mlp'])
+            # ---- update_fn (first Linear carries the folded second message Linear) + BN + act
+            if L['x_cat']:
+                H = ops.linear(S, L['Wu'], bias=L['c1'], row_scale=plan.degree(), row_vec=L['vf'],
+                               tab_idx=node_rows[:, 0].contiguous(), tab=L['Tu'], scale=L['su'], shift=L['tu'],
+                               activation=L['act_mlp'])
+            else:
+                H = ops.linear(x, L['Wu'], A2=S, bias=L['c1'], row_scale=plan.degree(), row_vec=L['vf'],
+                               scale=L['su'], shift=L['tu'], activation=L['act_mlp'])
+            # ---- second Linear + model-level BatchNorm + activation (models_graph_classification.py:231-233)
+            x = ops.linear(H, L['U2'], bias=L['c2'], scale=L['sm'], shift=L['tm'], activation=self._act_model)
+            x_interm.append(x)
+
+        out = None
+        mean = m.readout == 'mean'
+        for i, pr in enumerate(self.proj):
+            if pr is None:
+                continue
+            pooled = ops.pool_ptr(x_interm[i], node_ptr, mean)
+            if pr[0] == 'linear':
+                out = ops.linear(pooled, pr[1], bias=pr[2], out=out, accumulate=out is not None)
+            else:
+                _, W0, b0, s, t, W1, b1, act = pr
+                h = ops.linear(pooled, W0, bias=b0, scale=s, shift=t, activation=act)
+                out = ops.linear(h, W1, bias=b1, out=out, accumulate=out is not None)
+        return out

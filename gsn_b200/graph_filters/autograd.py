@@ -16,44 +16,12 @@ import torch
 from .. import ops
 
 
-class _SegmentSum(torch.autograd.Function):
-    """out[i] = sum_{e: key(e)=i} msgs[e]   (torch.sparse.sum(...).to_dense(), GSN_sparse.py:143)"""
-
-    @staticmethod
-    def forward(ctx, msgs, plan):
-        ctx.plan = plan
-        return ops.segment_sum(plan, msgs)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        plan = ctx.plan
-        key = plan.edge_index[plan.select]
-        return grad_out.contiguous().index_select(0, key), None
-
-
-class _GatherRows(torch.autograd.Function):
-    """rows[e] = x[index(e)] with index = edge_index[row]; backward is a
-    deterministic segment-sum grouped by that index."""
-
-    @staticmethod
-    def forward(ctx, x, edge_index, row, num_nodes):
-        ctx.args = (edge_index, row, num_nodes)
-        return x.index_select(0, edge_index[row])
-
-    @staticmethod
-    def backward(ctx, grad_rows):
-        edge_index, row, num_nodes = ctx.args
-        flow = 'target_to_source' if row == 0 else 'source_to_target'
-        plan = ops.edge_plan(edge_index, num_nodes, flow)       # grouped by edge_index[row]
-        return ops.segment_sum(plan, grad_rows.contiguous()), None, None, None
-
-
 def segment_sum(msgs, plan):
-    return _SegmentSum.apply(msgs, plan)
+    return ops.segment_sum_ad(plan, msgs)
 
 
 def gather_rows(x, edge_index, row):
-    return _GatherRows.apply(x, edge_index, row, x.shape[0])
+    return ops.gather_rows_ad(x, edge_index, row)
 
 
 def forward_with_grad(layer, x, edge_index, identifiers, ef):

@@ -123,3 +123,110 @@ class GNNSubstructures(nn.Module):
                 pooled = self.global_pool(x_interm[i], data.batch, num_graphs)
                 prediction = prediction + F.dropout(proj(pooled), p=self.dropout_features[i], training=self.training)
         return (prediction, x_interm) if return_intermediate else prediction
+
+
+class GNN_OGB(nn.Module):
+    """OGB variant (virtual node, residual, dropout) of
+    /root/reference/models_graph_classification_ogb_original.py:19-268: same constructor, sub-module
+    names and forward; layers are gsn_b200.graph_filters.{GSN,MPNN}_edge_sparse_ogb."""
+
+    def __init__(self, in_features, out_features, encoder_ids, d_in_id, in_edge_features=None,
+                 d_in_node_encoder=None, d_in_edge_encoder=None, encoder_degrees=None, d_degree=None, **kwargs):
+        super().__init__()
+        from .graph_filters import GSN_edge_sparse_ogb, MPNN_edge_sparse_ogb
+        kw = kwargs
+        seed = kw['seed']
+        self.model_name = kw['model_name']
+        self.readout = _default(kw['readout'], 'sum')
+        self.dropout_features, self.bn, self.final_projection = kw['dropout_features'], kw['bn'], kw['final_projection']
+        self.residual, self.inject_ids, self.vn = kw['residual'], kw['inject_ids'], kw['vn']
+        d_out, d_h = kw['d_out'], kw['d_h']
+        n_layers = len(d_out)
+        train_eps = _default(kw['train_eps'], [False] * n_layers)
+        act_mlp, bn_mlp = kw['activation_mlp'], kw['bn_mlp']
+        enc_kw = {'seed': seed, 'activation_mlp': act_mlp, 'bn_mlp': bn_mlp, 'aggr': kw['multi_embedding_aggr'],
+                  'features_scope': kw['features_scope']}
+        self.input_node_encoder = DiscreteEmbedding(kw['input_node_encoder'], in_features, d_in_node_encoder,
+                                                    kw['d_out_node_encoder'], **enc_kw)
+        d_in = self.input_node_encoder.d_out
+        if self.vn:
+            self.vn_encoder = DiscreteEmbedding(kw['input_vn_encoder'], 1, [1], kw['d_out_vn_encoder'],
+                                                **{**enc_kw, 'init': 'zeros'})
+            d_in_vn = self.vn_encoder.d_out
+        self.edge_encoder = nn.ModuleList(
+            DiscreteEmbedding(kw['edge_encoder'], in_edge_features, d_in_edge_encoder, kw['d_out_edge_encoder'][i], **enc_kw)
+            for i in range(n_layers))
+        self.id_encoder = nn.ModuleList(
+            DiscreteEmbedding(kw['id_embedding'], len(d_in_id), d_in_id, kw['d_out_id_embedding'], **enc_kw)
+            for _ in range(n_layers if self.inject_ids else 1))
+        degree_embedding = kw['degree_embedding'] if kw['degree_as_tag'][0] else 'None'
+        self.degree_encoder = DiscreteEmbedding(degree_embedding, 1, d_degree, kw['d_out_degree_embedding'], **enc_kw)
+
+        conv, norms, mlp_vn = [], [], []
+        for i in range(n_layers):
+            if i > 0 and self.vn:
+                mlp_vn.append(mlp(d_in_vn, kw['d_out_vn'][i - 1], d_h[i], seed, act_mlp, bn_mlp))
+                d_in_vn = kw['d_out_vn'][i - 1]
+            layer_kw = dict(d_in=d_in, d_degree=self.degree_encoder.d_out, degree_as_tag=kw['degree_as_tag'][i],
+                            retain_features=kw['retain_features'][i], d_msg=kw['d_msg'][i], d_up=d_out[i], d_h=d_h[i],
+                            seed=seed, activation_name=act_mlp, bn=bn_mlp, aggr=_default(kw['aggr'], 'add'),
+                            msg_kind=_default(kw['msg_kind'], 'general'), eps=0, train_eps=train_eps[i],
+                            flow=_default(kw['flow'], 'target_to_source'), d_ef=self.edge_encoder[i].d_out,
+                            edge_embedding=kw['edge_encoder'], id_embedding=kw['id_embedding'],
+                            extend_dims=kw['extend_dims'])
+            if (i == 0 or self.inject_ids) and self.model_name == 'GSN_edge_sparse_ogb':
+                layer_kw.update(d_id=self.id_encoder[i if self.inject_ids else 0].d_out, id_scope=kw['id_scope'])
+                conv.append(GSN_edge_sparse_ogb(**layer_kw))
+            else:
+                conv.append(MPNN_edge_sparse_ogb(**layer_kw))
+            norms.append(nn.BatchNorm1d(d_out[i]) if self.bn[i] else None)
+            d_in = d_out[i]
+        self.conv, self.batch_norms = nn.ModuleList(conv), nn.ModuleList(norms)
+        if self.vn:
+            self.mlp_vn = nn.ModuleList(mlp_vn)
+        pools = {'sum': global_add_pool_sparse, 'mean': global_mean_pool_sparse}
+        if self.readout not in pools:
+            raise ValueError('Invalid graph pooling type.')
+        self.global_pool = pools[self.readout]
+        if self.vn:
+            if kw['vn_pooling'] not in pools:
+                raise ValueError('Invalid graph virtual node pooling type.')
+            self.global_vn_pool = pools[kw['vn_pooling']]
+        self.lin_proj = nn.Linear(d_out[-1], out_features)
+        self.activation = choose_activation(kw['activation'])
+
+    def forward(self, data, return_intermediate=False):
+        layer_in = {'degrees': self.degree_encoder(data.degrees)}
+        edge_index, batch = data.edge_index, data.batch
+        num_graphs = getattr(data, 'num_graphs', None)
+        if num_graphs is None:
+            num_graphs = int(batch[-1].item()) + 1                         # :218
+        if self.vn:
+            vn = self.vn_encoder(torch.zeros(num_graphs, dtype=edge_index.dtype, device=edge_index.device))
+        x = self.input_node_encoder(data.x)
+        x_interm = [x]
+        last = len(self.conv) - 1
+        has_ef = hasattr(data, 'edge_features')
+        for i, conv in enumerate(self.conv):
+            layer_in['identifiers'] = self.id_encoder[i if self.inject_ids else 0](data.identifiers)
+            layer_in['edge_features'] = self.edge_encoder[i](data.edge_features) if has_ef else None
+            if self.vn:
+                x_interm[i] = x_interm[i] + vn[batch]
+            x = conv(x_interm[i], edge_index, **layer_in)
+            if self.bn[i]:
+                x = self.batch_norms[i](x)
+            if i != last:
+                x = self.activation(x)
+            x = F.dropout(x, self.dropout_features[i], training=self.training)
+            if self.residual:
+                x = x + x_interm[-1]
+            x_interm.append(x)
+            if i < last and self.vn:
+                vn_new = self.mlp_vn[i](self.global_vn_pool(x_interm[i], batch, num_graphs) + vn)
+                upd = F.dropout(self.activation(vn_new), self.dropout_features[i], training=self.training)
+                vn = vn_new + upd if self.residual else upd
+        total = 0
+        for i in range(len(self.conv) + 1):
+            if self.final_projection[i]:
+                total = total + x_interm[i]
+        return self.lin_proj(self.global_pool(total, batch, num_graphs))

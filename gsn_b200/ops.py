@@ -199,3 +199,138 @@ def general_edge_stats(plan: EdgePlan, P: torch.Tensor, Q: Optional[torch.Tensor
     with torch.cuda.device(plan.device):
         _lib.call('general_edge_stats', 'gsn_mp_general_edge_fwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr), plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), dh, None, None, 3, None, _lib.ptr(stats), _lib.stream_ptr())
     return stats
+
+
+
+# ----------------------------------------------------------------------------
+# dense tail + index fast path
+# ----------------------------------------------------------------------------
+class GsnLinear(ctypes.Structure):
+    """ctypes image of `struct GsnLinear` (include/gsn_b200.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ('A1', 'A2', 'W', 'bias', 'row_scale', 'row_vec', 'tab_idx', 'tab',
+                                               'scale', 'shift', 'C')] + \
+               [(n, ctypes.c_int32) for n in ('M', 'Nout', 'K1', 'K2', 'lda1', 'lda2', 'ldw', 'ldc', 'tab_ld', 'act',
+                                              'vec_ok', 'accumulate')]
+
+
+class GsnEncodeCol(ctypes.Structure):
+    """ctypes image of `struct GsnEncodeCol`."""
+    _fields_ = [('src', ctypes.c_void_p), ('stride', ctypes.c_int64), ('vocab_begin', ctypes.c_int32),
+                ('vocab_end', ctypes.c_int32), ('table_off', ctypes.c_int32), ('_pad', ctypes.c_int32)]
+
+
+def _dp(t):
+    return None if t is None else t.data_ptr()
+
+
+def linear(A1, W, bias=None, A2=None, row_scale=None, row_vec=None, tab_idx=None, tab=None, scale=None, shift=None,
+           activation='identity', out=None, accumulate=False):
+    """C = act((cat(A1,A2) @ W^T + row_scale (x) row_vec + tab[tab_idx] + bias) * scale + shift); see gsn_linear_fwd.
+    All tensors fp32 CUDA, last dim contiguous; W is [Nout, K1+K2] (nn.Linear layout)."""
+    M = (A1 if A1 is not None else (A2 if A2 is not None else tab_idx)).shape[0]
+    Nout = W.shape[0] if W is not None else tab.shape[1]
+    dev = (W if W is not None else tab).device
+    if out is None:
+        out = torch.empty((M, Nout), dtype=torch.float32, device=dev)
+    p = GsnLinear()
+    p.A1, p.A2, p.W = _dp(A1), _dp(A2), _dp(W)
+    p.K1 = 0 if A1 is None else A1.shape[1]
+    p.K2 = 0 if A2 is None else A2.shape[1]
+    p.lda1 = 0 if A1 is None else A1.stride(0)
+    p.lda2 = 0 if A2 is None else A2.stride(0)
+    p.ldw = 0 if W is None else W.stride(0)
+    if W is not None and W.shape[1] != p.K1 + p.K2:
+        raise ValueError(f'W has {W.shape[1]} columns, inputs have {p.K1}+{p.K2}')
+    p.bias, p.row_scale, p.row_vec = _dp(bias), _dp(row_scale), _dp(row_vec)
+    p.tab_idx, p.tab, p.tab_ld = _dp(tab_idx), _dp(tab), (0 if tab is None else tab.stride(0))
+    p.scale, p.shift, p.C, p.ldc = _dp(scale), _dp(shift), out.data_ptr(), out.stride(0)
+    p.M, p.Nout, p.act, p.accumulate = M, Nout, ACTIVATIONS[activation], int(bool(accumulate))
+    with torch.cuda.device(dev):
+        _lib.call('linear', 'gsn_linear_fwd', ctypes.byref(p), _lib.stream_ptr())
+    return out
+
+
+def pool_ptr(x, node_ptr, mean=False):
+    """sum / mean of the rows of every graph of a PyG batch (node_ptr = batch.ptr, int64 [G+1])"""
+    G = node_ptr.numel() - 1
+    x = _f32c(x, 'x')
+    out = torch.empty((G, x.shape[1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call('pool_ptr', 'gsn_pool_ptr', _lib.ptr(x), _lib.ptr(node_ptr), G, x.shape[1], x.stride(0), int(mean),
+                  _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def encode_rows(columns, vocab, num_rows, device):
+    """columns: list of (int64 tensor view [R] (any stride), (vocab_begin, vocab_end) or None, table_off).
+    Returns int32 [R, len(columns)] rows into a concatenated embedding table."""
+    cols = (GsnEncodeCol * len(columns))()
+    for i, (src, vr, off) in enumerate(columns):
+        if src.dtype != torch.int64:
+            raise ValueError('categorical columns must be int64')
+        cols[i].src, cols[i].stride = src.data_ptr(), (src.stride(0) if src.dim() else 1)
+        cols[i].vocab_begin, cols[i].vocab_end = (0, 0) if vr is None else (int(vr[0]), int(vr[1]))
+        cols[i].table_off = int(off)
+    out = torch.empty((num_rows, len(columns)), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.call('encode_rows', 'gsn_encode_rows', ctypes.cast(cols, ctypes.c_void_p), len(columns), _lib.ptr(vocab),
+                  num_rows, _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def general_edge_idx(plan, dh, P=None, Q=None, node_rows=None, Tn=None, edge_rows=None, Te=None, scale=None, shift=None,
+                     activation='relu'):
+    """S[i] = sum_e act((P_i + P_j + sum Tn[node rows] + Q_e + sum Te[edge rows]) * scale + shift)"""
+    S = torch.empty((plan.N, dh), dtype=torch.float32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _lib.call('general_edge', 'gsn_mp_general_edge_idx_fwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid),
+                  _lib.ptr(plan.nbr), plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), _lib.ptr(node_rows),
+                  0 if node_rows is None else node_rows.shape[1], _lib.ptr(Tn), _lib.ptr(edge_rows),
+                  0 if edge_rows is None else edge_rows.shape[1], _lib.ptr(Te), dh, _lib.ptr(scale), _lib.ptr(shift),
+                  ACTIVATIONS[activation], _lib.ptr(S), _lib.stream_ptr())
+    return S
+
+
+# ----------------------------------------------------------------------------
+# differentiable wrappers (training): backward of a segment-sum is a gather,
+# backward of a gather is a segment-sum over the grouping by the gather index
+# ----------------------------------------------------------------------------
+class _SegmentSumFn(torch.autograd.Function):
+    """out[i] = sum_{e: key(e)=i} rows[e]   (torch.sparse.sum(...).to_dense(), GSN_sparse.py:143)"""
+
+    @staticmethod
+    def forward(ctx, rows, plan):
+        ctx.plan = plan
+        return segment_sum(plan, rows)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        plan = ctx.plan
+        return grad_out.contiguous().index_select(0, plan.edge_index[plan.select]), None
+
+
+class _GatherRowsFn(torch.autograd.Function):
+    """rows[e] = x[edge_index[row][e]]; backward = deterministic segment-sum grouped by that index"""
+
+    @staticmethod
+    def forward(ctx, x, edge_index, row, num_nodes):
+        ctx.args = (edge_index, row, num_nodes)
+        return x.index_select(0, edge_index[row])
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        edge_index, row, num_nodes = ctx.args
+        plan = edge_plan(edge_index, num_nodes, 'target_to_source' if row == 0 else 'source_to_target')
+        return segment_sum(plan, grad_rows.contiguous()), None, None, None
+
+
+def segment_sum_ad(plan: EdgePlan, rows: torch.Tensor) -> torch.Tensor:
+    if torch.is_grad_enabled() and rows.requires_grad:
+        return _SegmentSumFn.apply(rows, plan)
+    return segment_sum(plan, rows)
+
+
+def gather_rows_ad(x: torch.Tensor, edge_index: torch.Tensor, row: int) -> torch.Tensor:
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _GatherRowsFn.apply(x, edge_index, row, x.shape[0])
+    return x.index_select(0, edge_index[row])

@@ -52,8 +52,12 @@ class Batch:
 class GSNPipeline:
 
     def __init__(self, model, subgraph_dicts, induced: bool, id_scope: str, encoder: UniqueEncoder,
-                 max_nodes_per_graph: int):
+                 max_nodes_per_graph: int, fused: bool = True):
+        from . import fused as _fused
         self.model, self.subgraph_dicts, self.induced, self.id_scope = model, subgraph_dicts, induced, id_scope
+        # inference fast path (indices instead of one-hot tensors, BN folded, own GEMM kernels) when the
+        # model configuration allows it; otherwise the per-layer path
+        self.fused = _fused.FusedForward(model) if (fused and _fused.supported(model) and not model.training) else None
         self.encoder, self.max_nodes = encoder, int(max_nodes_per_graph)
         self.n_cols = total_columns(subgraph_dicts)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
@@ -71,6 +75,10 @@ class GSNPipeline:
         ids = counting.count_batch(t['edge_index'], t['node_ptr'], self.subgraph_dicts, self.induced, self.id_scope,
                                    num_nodes=N, max_nodes_per_graph=self.max_nodes, check=False, graph=graph)
         self.last_status = graph.status
+        if self.fused is not None:
+            data = Batch(x=t['x'], edge_index=t['edge_index'], edge_features=t['edge_features'], batch=t['batch'],
+                         degrees=t['degrees'], node_ptr=t['node_ptr'], num_graphs=G)
+            return self.fused(data, raw_identifiers=ids, vocab=self.encoder.vocab)
         data = Batch(x=t['x'], edge_index=t['edge_index'], edge_features=t['edge_features'], batch=t['batch'],
                      degrees=t['degrees'], identifiers=self.encoder(ids), num_graphs=G)
         return self.model(data)

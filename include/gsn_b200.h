@@ -212,6 +212,75 @@ int gsn_mp_general_edge_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const
                             const float *d_shift, int32_t act, float *d_S, double *d_stats, void *stream);
 
 /* ------------------------------------------------------------------ */
+/* dense tail + index ("one-hot free") fast path                      */
+/* ------------------------------------------------------------------ */
+
+/*
+ * Fused Linear of models_misc.py:52-59 (update_fn, JK projections, the N-row halves
+ * of the split msg_fn):
+ *   C[m,n] = act( ( sum_k A1[m,k] W[n,k] + sum_k A2[m,k] W[n,K1+k]        cat(A1,A2) @ W^T, no cat tensor
+ *                   + row_scale[m]*row_vec[n]                              deg_i * (W b2): bias of the summed messages
+ *                   + tab[tab_idx[m], n]                                   one-hot input block folded into a table
+ *                   + bias[n] ) * scale[n] + shift[n] )                    BatchNorm1d (eval) as scale/shift
+ * W: nn.Linear layout [Nout, K1+K2], row stride ldw.  Optional pointers may be NULL
+ * (row_scale/row_vec and tab/tab_idx come in pairs).  act: 0 relu, 1 elu, 2 tanh, 3 identity.
+ * fp32 FFMA accumulation.  `vec_ok` is filled in by the library.
+ */
+typedef struct GsnLinear {
+    const float *A1; const float *A2; const float *W;
+    const float *bias; const float *row_scale; const float *row_vec;
+    const int32_t *tab_idx; const float *tab;
+    const float *scale; const float *shift;
+    float *C;
+    int32_t M, Nout, K1, K2, lda1, lda2, ldw, ldc, tab_ld, act, vec_ok;
+    int32_t accumulate;      /* 1: C += result (sum of JK projections, models_graph_classification.py:236-240) */
+} GsnLinear;
+
+int gsn_linear_fwd(const GsnLinear *h_p, void *stream);
+
+/*
+ * out[g,:] = sum (mean=1: average) of the rows x[ptr[g] .. ptr[g+1]) : the readouts
+ * global_add_pool_sparse / global_mean_pool_sparse (utils_graph_learning.py:23-41) for a
+ * PyG batch whose nodes are grouped by graph (ptr = batch.ptr).
+ */
+int gsn_pool_ptr(const float *d_x, const int64_t *d_ptr, int64_t G, int32_t d, int32_t ldx, int32_t mean,
+                 float *d_out, void *stream);
+
+/*
+ * Categorical columns -> rows of one concatenated embedding table (replaces
+ * one_hot_unique + one_hot_encoder + the first Linear's one-hot block,
+ * utils_encoding.py:37-59 / utils_graph_learning.py:170-187):
+ *   out[r, c] = table_off[c] + rank_c(src_c[r * stride_c])
+ * rank_c = position of the value among the sorted distinct values vocab[vocab_ptr[c] .. vocab_ptr[c+1])
+ * (one_hot_unique; clamped to the last entry), or the value itself when the range is empty.
+ */
+typedef struct GsnEncodeCol {
+    const int64_t *src;      /* device */
+    int64_t stride;          /* elements between consecutive rows */
+    int32_t vocab_begin, vocab_end;   /* into d_vocab; begin == end: identity */
+    int32_t table_off, _pad;
+} GsnEncodeCol;
+
+#define GSN_MAX_ENCODE_COLS 16
+int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d_vocab, int64_t R, int32_t *d_out,
+                    void *stream);
+
+/*
+ * 'general' message kind with categorical inputs kept as indices (layer 0 of the ZINC /
+ * IMDB recipes: x, edge features and identifiers are one-hot, so the first Linear of msg_fn
+ * is a sum of table rows):
+ *   h_e = [P[i,0:dh] + P[nbr,dh:2dh]]  +  sum_c Tn[node_rows[i,c], 0:dh] + sum_c Tn[node_rows[nbr,c], dh:2dh]
+ *       + [Q[e,:]] + sum_c Te[edge_rows[e,c], :]
+ *   S[i] = sum_{e in row i} act(h_e * scale + shift)
+ * Any of the dense (P, Q) and indexed (node_rows/Tn, edge_rows/Te) parts may be NULL.
+ */
+int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                                int64_t E, const float *d_P, const float *d_Q, const int32_t *d_node_rows,
+                                int32_t n_node_cols, const float *d_Tn, const int32_t *d_edge_rows, int32_t n_edge_cols,
+                                const float *d_Te, int32_t dh, const float *d_scale, const float *d_shift, int32_t act,
+                                float *d_S, void *stream);
+
+/* ------------------------------------------------------------------ */
 /* misc                                                                */
 /* ------------------------------------------------------------------ */
 int gsn_abi_version(void);
