@@ -182,6 +182,11 @@ def run_ours(args, rank, world, local_rank):
         my_launches_per_step = _lib.launch_count() - l0
     out = pipe.replay().clone()
     torch.cuda.synchronize()
+    if os.environ.get('GSN_PROFILE_REPLAY'):      # ncu --profile-from-start off --graph-profiling node
+        torch.cuda.profiler.start()
+        pipe.replay()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     assert torch.allclose(out, ref_out, atol=1e-5, rtol=1e-5), 'captured step differs from eager step'
     assert int(pipe.last_status.item()) == 0
 

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) linear_kernel(const __g
     __shared__ __align__(16) float Bs[2][BK][BN + 4];
 
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int K = p.K1 + p.K2;
     const int tx = tid % (BN / TN), ty = tid / (BN / TN);
 
@@ -199,13 +199,13 @@ extern "C" int gsn_linear_fwd(const GsnLinear *h_p, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t tiles64 = ceil_div(p.M, 64) * ceil_div(p.Nout, 64);
     if (tiles64 >= 4 * kNumSMs && p.Nout >= 96) {
-        dim3 grid((unsigned)ceil_div(p.Nout, 128), (unsigned)ceil_div(p.M, 128));
+        dim3 grid((unsigned)ceil_div(p.M, 128), (unsigned)ceil_div(p.Nout, 128));
         linear_kernel<128, 128, 8, 8><<<grid, 256, 0, stream>>>(p);
     } else if (tiles64 >= kNumSMs / 2) {
-        dim3 grid((unsigned)ceil_div(p.Nout, 64), (unsigned)ceil_div(p.M, 64));
+        dim3 grid((unsigned)ceil_div(p.M, 64), (unsigned)ceil_div(p.Nout, 64));
         linear_kernel<64, 64, 4, 4><<<grid, 256, 0, stream>>>(p);
     } else {
-        dim3 grid((unsigned)ceil_div(p.Nout, 64), (unsigned)ceil_div(p.M, 16));
+        dim3 grid((unsigned)ceil_div(p.M, 16), (unsigned)ceil_div(p.Nout, 64));
         linear_kernel<16, 64, 4, 4><<<grid, 64, 0, stream>>>(p);
     }
     GSN_BUMP(1);

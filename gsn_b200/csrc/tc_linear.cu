@@ -1,0 +1,346 @@
+// Tensor-core version of the dense tail (gsn_linear_fwd semantics) for sm_100a:
+// tcgen05.mma kind::tf32 with the accumulator in TMEM, operands staged by TMA
+// (cp.async.bulk.tensor, SWIZZLE_128B) through a 3-stage mbarrier ring.
+//
+// fp32 parity (1e-5, BASELINE.json) rules out plain TF32 (10-bit mantissa), so
+// every product is evaluated as 3xTF32:
+//     a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi ,  x_hi = rn_tf32(x), x_lo = rn_tf32(x - x_hi)
+// accumulated in fp32 in TMEM; every dropped term is <= 2^-22 relative and unbiased.
+// Weights are split once (cached by the host side); activations are split by
+// split_a_kernel into one [M, K1+K2] hi/lo pair (this also performs the
+// torch.cat((x, agg)) of graph_filters/GSN_edge_sparse.py:111).
+//
+// Warp roles (256 threads, one 128 x BN output tile per CTA):
+//   warp 0 lane 0 : TMA producer          warp 1 lane 0 : MMA issuer
+//   warp 2        : TMEM alloc / dealloc  warps 4..7    : epilogue (tcgen05.ld -> registers -> global)
+#include <cuda.h>
+#include "common.cuh"
+
+namespace gsn {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;        // 32 fp32 = 128 bytes = one SWIZZLE_128B row
+constexpr int TC_UMMA_K = 8;     // tf32
+
+struct TcEpilogue {
+    const float *bias, *row_scale, *row_vec, *tab, *scale, *shift;
+    const int32_t *tab_idx;
+    float *C;
+    int M, Nout, K, ldc, tab_ld, act, accumulate;
+};
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+    switch (act) {
+        case 0: return fmaxf(v, 0.0f);
+        case 1: return v > 0.0f ? v : expm1f(v);
+        case 2: return tanhf(v);
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(const void *smem_tile) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);      // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                     // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                           // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                                     // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                     // layout: SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                 const __grid_constant__ TcEpilogue ep) {
+    constexpr int A_TILE = TC_BM * TC_BK * 4;      // bytes
+    constexpr int W_TILE = BN * TC_BK * 4;
+    constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+    const int nk = (ep.K + TC_BK - 1) / TC_BK;
+    // 1024-byte aligned base of the stage ring (SWIZZLE_128B atoms)
+    unsigned char *ring = (unsigned char *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_lo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"((uint32_t)(2 * BN))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            unsigned char *st = ring + (size_t)s * STAGE;
+            mbar_arrive_expect_tx(&full_bar[s], STAGE);
+            const int k0 = kt * TC_BK;
+            tma_load_2d(st, &tmA_hi, k0, m0, &full_bar[s]);
+            tma_load_2d(st + A_TILE, &tmA_lo, k0, m0, &full_bar[s]);
+            tma_load_2d(st + 2 * A_TILE, &tmW_hi, k0, n0, &full_bar[s]);
+            tma_load_2d(st + 2 * A_TILE + W_TILE, &tmW_lo, k0, n0, &full_bar[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer
+        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            unsigned char *st = ring + (size_t)s * STAGE;
+            const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + A_TILE);
+            const uint64_t w_hi = umma_desc(st + 2 * A_TILE), w_lo = umma_desc(st + 2 * A_TILE + W_TILE);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);      // 32 bytes per k-step inside the swizzle row
+                const uint32_t first = (kt > 0 || k > 0) ? 1u : 0u;
+                // The tensor core adds into the fp32 accumulator with truncation, a bias that grows with the
+                // number of accumulations: the two correction terms (2^-11 of the main one) therefore get their
+                // own accumulator (columns [BN, 2BN)) and are added once, in the epilogue.
+                umma_tf32(tmem_d, a_hi + adv, w_hi + adv, idesc, first);
+                umma_tf32(tmem_d + BN, a_lo + adv, w_hi + adv, idesc, first);
+                umma_tf32(tmem_d + BN, a_hi + adv, w_lo + adv, idesc, 1u);
+            }
+            umma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
+        }
+        umma_commit(&tmem_full_bar);             // accumulator complete
+    } else if (warp >= 4) {
+        // ---------------- epilogue: TMEM lane = output row
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int wq = warp - 4;                 // == warp % 4: the TMEM lane quarter this warp may access
+        const int m = m0 + wq * 32 + lane;
+        const float rs = (ep.row_scale && m < ep.M) ? __ldg(ep.row_scale + m) : 0.f;
+        const float *trow = (ep.tab && m < ep.M) ? ep.tab + (int64_t)__ldg(ep.tab_idx + m) * ep.tab_ld : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32], q[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+                  "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]),
+                  "=r"(q[16]), "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]),
+                  "=r"(q[24]), "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+                : "r"(taddr + (uint32_t)BN)
+                : "memory");
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (m < ep.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < ep.Nout) {
+                        float v = __uint_as_float(r[j]) + __uint_as_float(q[j]);
+                        if (ep.row_vec) v = fmaf(rs, __ldg(ep.row_vec + n), v);
+                        if (trow) v += __ldg(trow + n);
+                        if (ep.bias) v += __ldg(ep.bias + n);
+                        if (ep.scale) v = fmaf(v, __ldg(ep.scale + n), ep.shift ? __ldg(ep.shift + n) : 0.f);
+                        else if (ep.shift) v += __ldg(ep.shift + n);
+                        v = tc_act(v, ep.act);
+                        float *dst = ep.C + (int64_t)m * ep.ldc + n;
+                        *dst = ep.accumulate ? *dst + v : v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
+// x -> (rn_tf32(x), x - rn_tf32(x)) ; two row-major sources concatenated along K into [M, K1+K2]
+__global__ void split_a_kernel(const float *__restrict__ A1, int K1, int lda1, const float *__restrict__ A2, int K2,
+                               int lda2, int64_t M, float *__restrict__ hi, float *__restrict__ lo) {
+    const int K = K1 + K2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one float4 each
+    const int kq = K / 4;
+    if (t >= M * kq) return;
+    const int64_t m = t / kq;
+    const int k = (int)(t % kq) * 4;
+    float4 v = k < K1 ? __ldg(reinterpret_cast<const float4 *>(A1 + m * lda1 + k))
+                      : __ldg(reinterpret_cast<const float4 *>(A2 + m * lda2 + (k - K1)));
+    float a[4] = {v.x, v.y, v.z, v.w}, h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a[i]));
+        h[i] = __uint_as_float(u);
+        // the residual is rounded (not left for the tensor core to truncate): truncation is biased and its
+        // error grows linearly with K, rounding keeps it a random walk
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a[i] - h[i]));
+        l[i] = __uint_as_float(u);
+    }
+    *reinterpret_cast<float4 *>(hi + m * K + k) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4 *>(lo + m * K + k) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// fp32 row-major [rows, cols] (row stride ld elements), box = [box_rows, 32 cols], 128-byte swizzle, OOB -> 0
+static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return GSN_E_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled failed: %d", (int)r);
+        return GSN_E_CUDA;
+    }
+    return GSN_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &w_hi, const CUtensorMap &w_lo,
+                     const TcEpilogue &ep, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid((unsigned)ceil_div(ep.M, TC_BM), (unsigned)ceil_div(ep.Nout, BN));
+    tc_linear_kernel<BN, STAGES><<<grid, 256, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, ep);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("tc_linear_kernel");
+    return GSN_OK;
+}
+
+}  // namespace gsn
+
+using namespace gsn;
+
+extern "C" int gsn_split_tf32(const float *d_src, int64_t rows, int32_t cols, int32_t ld, float *d_hi, float *d_lo,
+                              void *stream_) {
+    if (rows < 0 || cols < 4 || cols % 4 || ld % 4 || !d_src || !d_hi || !d_lo) return GSN_E_INVALID;
+    if (rows == 0) return GSN_OK;
+    const int64_t n4 = rows * (cols / 4);
+    split_a_kernel<<<(unsigned)ceil_div(n4, 256), 256, 0, (cudaStream_t)stream_>>>(d_src, cols, ld, nullptr, 0, 0, rows, d_hi, d_lo);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_split_tf32");
+    return GSN_OK;
+}
+
+extern "C" int gsn_tc_linear_workspace_bytes(int64_t M, int32_t K, size_t *bytes) {
+    if (!bytes || M < 0 || K < 0) return GSN_E_INVALID;
+    *bytes = 2 * align_up(sizeof(float) * (size_t)M * (size_t)K, 1024) + 1024;
+    return GSN_OK;
+}
+
+extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const float *d_Wlo, void *d_ws, size_t ws_bytes,
+                                 void *stream_) {
+    if (!h_p || !d_Whi || !d_Wlo || !d_ws) return GSN_E_INVALID;
+    const GsnLinear &p = *h_p;
+    const int K = p.K1 + p.K2;
+    if (p.M < 0 || p.Nout < 1 || K < 4 || !p.C || !p.A1) return GSN_E_INVALID;
+    auto al16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+    if (p.K1 % 4 || p.K2 % 4 || p.lda1 % 4 || (p.K2 > 0 && (p.lda2 % 4 || !p.A2)) || !al16(p.A1) || !al16(p.A2) ||
+        !al16(d_Whi) || !al16(d_Wlo))
+        return GSN_E_UNSUPPORTED;
+    if ((p.row_scale == nullptr) != (p.row_vec == nullptr) || (p.tab == nullptr) != (p.tab_idx == nullptr)) return GSN_E_INVALID;
+    if (p.M == 0) return GSN_OK;
+    size_t need = 0;
+    gsn_tc_linear_workspace_bytes(p.M, K, &need);
+    if (ws_bytes < need) return GSN_E_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    float *a_hi = (float *)(((uintptr_t)d_ws + 1023) & ~(uintptr_t)1023);
+    float *a_lo = a_hi + align_up(sizeof(float) * (size_t)p.M * K, 1024) / sizeof(float);
+    const int64_t n4 = (int64_t)p.M * (K / 4);
+    split_a_kernel<<<(unsigned)ceil_div(n4, 256), 256, 0, stream>>>(p.A1, p.K1, p.lda1, p.A2, p.K2, p.lda2, p.M, a_hi, a_lo);
+    GSN_BUMP(1);
+    const int BN = p.Nout > 128 ? 256 : (p.Nout > 64 ? 128 : 64);
+    CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
+    int rc;
+    if ((rc = make_map(&mA_hi, a_hi, p.M, K, K, TC_BM))) return rc;
+    if ((rc = make_map(&mA_lo, a_lo, p.M, K, K, TC_BM))) return rc;
+    if ((rc = make_map(&mW_hi, d_Whi, p.Nout, K, K, BN))) return rc;
+    if ((rc = make_map(&mW_lo, d_Wlo, p.Nout, K, K, BN))) return rc;
+    TcEpilogue ep{p.bias, p.row_scale, p.row_vec, p.tab, p.scale, p.shift, p.tab_idx, p.C,
+                  p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate};
+    if (BN == 256) return launch_tc<256, 2>(mA_hi, mA_lo, mW_hi, mW_lo, ep, stream);
+    if (BN == 128) return launch_tc<128, 3>(mA_hi, mA_lo, mW_hi, mW_lo, ep, stream);
+    return launch_tc<64, 4>(mA_hi, mA_lo, mW_hi, mW_lo, ep, stream);
+}

@@ -223,6 +223,40 @@ def _dp(t):
     return None if t is None else t.data_ptr()
 
 
+# Tensor-core dense tail (tcgen05 3xTF32).  "auto": use it whenever the shapes allow (K % 4 == 0, aligned).
+TENSOR_CORES = 'auto'       # 'auto' | 'off'
+_wsplit_cache = {}
+
+
+def split_weight(W: torch.Tensor):
+    """(W_hi, W_lo) tf32 split of a weight matrix, cached per (storage, version)"""
+    key = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0))
+    hit = _wsplit_cache.get(key)
+    if hit is None:
+        hi = torch.empty((W.shape[0], W.shape[1]), dtype=torch.float32, device=W.device)
+        lo = torch.empty_like(hi)
+        with torch.cuda.device(W.device):
+            _lib.call('split_tf32', 'gsn_split_tf32', _lib.ptr(W), W.shape[0], W.shape[1], W.stride(0), _lib.ptr(hi),
+                      _lib.ptr(lo), _lib.stream_ptr())
+        if len(_wsplit_cache) > 256:
+            _wsplit_cache.clear()
+        hit = (hi, lo, W)           # keep W alive so the data_ptr key cannot be recycled
+        _wsplit_cache[key] = hit
+    return hit[0], hit[1]
+
+
+def _tc_eligible(A1, A2, W):
+    if TENSOR_CORES == 'off' or W is None or A1 is None:
+        return False
+    K1 = A1.shape[1]
+    K2 = 0 if A2 is None else A2.shape[1]
+    if K1 % 4 or K2 % 4 or (K1 + K2) < 8 or A1.stride(0) % 4 or (A2 is not None and A2.stride(0) % 4) or W.stride(0) % 4:
+        return False
+    if A1.data_ptr() % 16 or (A2 is not None and A2.data_ptr() % 16) or W.data_ptr() % 16:
+        return False
+    return A1.shape[0] >= 1
+
+
 def linear(A1, W, bias=None, A2=None, row_scale=None, row_vec=None, tab_idx=None, tab=None, scale=None, shift=None,
            activation='identity', out=None, accumulate=False):
     """C = act((cat(A1,A2) @ W^T + row_scale (x) row_vec + tab[tab_idx] + bias) * scale + shift); see gsn_linear_fwd.
@@ -246,7 +280,15 @@ def linear(A1, W, bias=None, A2=None, row_scale=None, row_vec=None, tab_idx=None
     p.scale, p.shift, p.C, p.ldc = _dp(scale), _dp(shift), out.data_ptr(), out.stride(0)
     p.M, p.Nout, p.act, p.accumulate = M, Nout, ACTIVATIONS[activation], int(bool(accumulate))
     with torch.cuda.device(dev):
-        _lib.call('linear', 'gsn_linear_fwd', ctypes.byref(p), _lib.stream_ptr())
+        if _tc_eligible(A1, A2, W):
+            whi, wlo = split_weight(W)
+            nb = ctypes.c_size_t(0)
+            _lib.check(_lib.lib().gsn_tc_linear_workspace_bytes(M, p.K1 + p.K2, ctypes.byref(nb)), 'gsn_tc_linear_workspace_bytes')
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            _lib.call('tc_linear', 'gsn_tc_linear_fwd', ctypes.byref(p), _lib.ptr(whi), _lib.ptr(wlo), _lib.ptr(ws),
+                      nb.value, _lib.stream_ptr())
+        else:
+            _lib.call('linear', 'gsn_linear_fwd', ctypes.byref(p), _lib.stream_ptr())
     return out
 
 

@@ -239,6 +239,20 @@ typedef struct GsnLinear {
 int gsn_linear_fwd(const GsnLinear *h_p, void *stream);
 
 /*
+ * Tensor-core (tcgen05, TMEM accumulator, TMA-staged operands) version of gsn_linear_fwd with
+ * fp32-equivalent accuracy through 3xTF32 (a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi).
+ *   gsn_split_tf32           x -> (rn_tf32(x), x - rn_tf32(x)), [rows, cols] with row stride ld -> dense [rows, cols];
+ *                            used once per weight matrix (W in nn.Linear layout [Nout, K1+K2])
+ *   gsn_tc_linear_fwd        same meaning as gsn_linear_fwd; d_Whi / d_Wlo are the split weights; d_ws holds the
+ *                            split activations (gsn_tc_linear_workspace_bytes).  Needs K1, K2, lda1, lda2 % 4 == 0
+ *                            and 16-byte aligned operands, otherwise GSN_E_UNSUPPORTED (use gsn_linear_fwd).
+ */
+int gsn_split_tf32(const float *d_src, int64_t rows, int32_t cols, int32_t ld, float *d_hi, float *d_lo, void *stream);
+int gsn_tc_linear_workspace_bytes(int64_t M, int32_t K, size_t *bytes);
+int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const float *d_Wlo, void *d_ws, size_t ws_bytes,
+                      void *stream);
+
+/*
  * out[g,:] = sum (mean=1: average) of the rows x[ptr[g] .. ptr[g+1]) : the readouts
  * global_add_pool_sparse / global_mean_pool_sparse (utils_graph_learning.py:23-41) for a
  * PyG batch whose nodes are grouped by graph (ptr = batch.ptr).
