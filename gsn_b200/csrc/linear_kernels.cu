@@ -17,13 +17,12 @@
 
 namespace gsn {
 
+// elu / tanh out of line: inlined into the unrolled epilogue they bloat it into an instruction-fetch-bound blob
+__device__ __noinline__ float act_slow(float v, int act) {
+    return act == 1 ? (v > 0.0f ? v : expm1f(v)) : tanhf(v);
+}
 __device__ __forceinline__ float act_apply(float v, int act) {
-    switch (act) {
-        case 0: return fmaxf(v, 0.0f);
-        case 1: return v > 0.0f ? v : expm1f(v);
-        case 2: return tanhf(v);
-        default: return v;
-    }
+    return act == 0 ? fmaxf(v, 0.0f) : (act == 3 ? v : act_slow(v, act));
 }
 
 template <int BM, int BN, int TM, int TN>
@@ -143,6 +142,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) linear_kernel(const __g
     }
 
     // ---- epilogue
+    const bool accumulate = p.accumulate != 0;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const int m = m0 + ty * TM + i;
@@ -161,7 +161,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) linear_kernel(const __g
             else if (p.shift) v += __ldg(p.shift + n);
             v = act_apply(v, p.act);
             float *dst = p.C + (int64_t)m * p.ldc + n;
-            *dst = p.accumulate ? *dst + v : v;
+            if (accumulate) v += *dst;              // a real branch: `cond ? *dst + v : v` makes the load unconditional
+            *dst = v;
         }
     }
 }

@@ -238,13 +238,12 @@ struct GenParams {
 };
 
 // choose_activation of models_misc.py:5-15
+__device__ __noinline__ float apply_act_slow(float v, int act) {
+    return act == 1 ? (v > 0.0f ? v : expm1f(v))             // elu (alpha = 1)
+                    : tanhf(v);                              // tanh
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
-    switch (act) {
-        case 0: return fmaxf(v, 0.0f);                       // relu
-        case 1: return v > 0.0f ? v : expm1f(v);             // elu (alpha = 1)
-        case 2: return tanhf(v);                             // tanh
-        default: return v;                                   // identity
-    }
+    return act == 0 ? fmaxf(v, 0.0f) : (act == 3 ? v : apply_act_slow(v, act));   // relu / identity inline
 }
 
 template <int VEC, bool STATS>

@@ -278,7 +278,7 @@ def linear(A1, W, bias=None, A2=None, row_scale=None, row_vec=None, tab_idx=None
     p.bias, p.row_scale, p.row_vec = _dp(bias), _dp(row_scale), _dp(row_vec)
     p.tab_idx, p.tab, p.tab_ld = _dp(tab_idx), _dp(tab), (0 if tab is None else tab.stride(0))
     p.scale, p.shift, p.C, p.ldc = _dp(scale), _dp(shift), out.data_ptr(), out.stride(0)
-    p.M, p.Nout, p.act, p.accumulate = M, Nout, ACTIVATIONS[activation], int(bool(accumulate))
+    p.M, p.Nout, p.act, p.accumulate = M, Nout, ACTIVATIONS[activation], int(accumulate)
     with torch.cuda.device(dev):
         if _tc_eligible(A1, A2, W):
             whi, wlo = split_weight(W)

@@ -251,6 +251,8 @@ int gsn_split_tf32(const float *d_src, int64_t rows, int32_t cols, int32_t ld, f
 int gsn_tc_linear_workspace_bytes(int64_t M, int32_t K, size_t *bytes);
 int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const float *d_Wlo, void *d_ws, size_t ws_bytes,
                       void *stream);
+/* Profiling aid: non-NULL -> every tc_linear CTA writes 8 clock64 stamps to d_buf[cta*8..]; NULL disables. */
+int gsn_tc_debug_buffer(void *d_buf);
 
 /*
  * out[g,:] = sum (mean=1: average) of the rows x[ptr[g] .. ptr[g+1]) : the readouts
