@@ -194,5 +194,58 @@ def make_mp(out_dir):
     torch.save(mg, os.path.join(out_dir, 'mp_models.pt'))
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and (len(sys.argv) < 2 or sys.argv[1] != 'sr'):
     make_mp(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden'))
+
+
+def make_sr_isomorphism(out_dir):
+    """README.md:84 recipe on SR(25,12,5,6) with the reference's own model class and seed-0 initialisation:
+    stores the weights and the 15 graph embeddings (test_isomorphism, train_test_funcs.py:262-277)."""
+    import numpy as np
+    from oracle import count_c, count_vf2, ref_import
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests'))
+    z = np.load(os.path.join(out_dir, 'sr251256.npz'))
+    eis = z['edge_index'].astype(np.int64)
+    node_ptr = np.arange(16, dtype=np.int64) * 25
+    edge_ptr = np.arange(16, dtype=np.int64) * 300
+    ei = np.concatenate([eis[i] + 25 * i for i in range(15)], 1)
+    sds = count_vf2.make_subgraph_dicts(count_vf2.pattern_edge_lists('cycle_graph', 6), 'local')
+    ids = count_c.count_batch(node_ptr, edge_ptr, ei, sds, True, 1)
+    ranks = np.stack([np.unique(ids[:, c], return_inverse=True)[1] for c in range(ids.shape[1])], 1)
+    d_id = [int(len(np.unique(ids[:, c]))) for c in range(ids.shape[1])]
+    M = ref_import.models()
+    L, d = 2, 64
+    args = dict(seed=0, model_name='GSN_sparse', readout='sum', dropout_features=[0.0] * (L + 1), bn=[False] * L,
+                final_projection=[False] * L + [True], inject_ids=False, inject_edge_features=True, random_features=False,
+                id_scope='local', d_msg=[d] * L, d_out=[d] * L, d_h=[[d]] * L, aggr='add', flow='source_to_target',
+                msg_kind='general', train_eps=[False] * L, activation_mlp='relu', bn_mlp=True, jk_mlp=True,
+                degree_embedding='one_hot_encoder', degree_as_tag=[False] * L, retain_features=[False, True],
+                multi_embedding_aggr='sum', input_node_encoder='None', d_out_node_encoder=d, edge_encoder='None',
+                d_out_edge_encoder=[d] * L, id_embedding='one_hot_encoder', d_out_id_embedding=d,
+                d_out_degree_embedding=d, extend_dims=True, activation='relu')
+    ctor = dict(in_features=1, out_features=2, encoder_ids=None, d_in_id=d_id, in_edge_features=None,
+                d_in_node_encoder=None, d_in_edge_encoder=None, encoder_degrees=None, d_degree=None)
+    torch.manual_seed(0)                                   # main.py:43-50
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = M['GNNSubstructures'](**ctor, **args)
+    model.eval()
+
+    class Obj:
+        pass
+    dobj = Obj()
+    dobj.x = torch.ones((375, 1))
+    dobj.edge_index = torch.from_numpy(ei)
+    dobj.identifiers = torch.from_numpy(ranks)
+    dobj.degrees = torch.full((375,), 12.0)
+    dobj.batch = torch.repeat_interleave(torch.arange(15), 25)
+    warnings.filterwarnings('ignore')
+    with torch.no_grad():
+        y = model(dobj)
+    mm = torch.pdist(y, p=2)
+    print('SR isomorphism: d_id', d_id, 'failures', int((mm < 1e-2).sum()), 'of', mm.numel(), 'min dist', float(mm.min()))
+    torch.save({'ctor': ctor, 'args': args, 'state_dict': model.state_dict(), 'y': y, 'identifiers': torch.from_numpy(ids)},
+               os.path.join(out_dir, 'sr_isomorphism.pt'))
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'sr':
+    make_sr_isomorphism(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden'))
