@@ -194,7 +194,7 @@ def make_mp(out_dir):
     torch.save(mg, os.path.join(out_dir, 'mp_models.pt'))
 
 
-if __name__ == '__main__' and (len(sys.argv) < 2 or sys.argv[1] != 'sr'):
+if __name__ == '__main__' and (len(sys.argv) < 2 or sys.argv[1] not in ('sr', 'ogb')):
     make_mp(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden'))
 
 
@@ -249,3 +249,75 @@ def make_sr_isomorphism(out_dir):
 
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'sr':
     make_sr_isomorphism(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden'))
+
+
+def make_ogb(out_dir):
+    """GNN_OGB (models_graph_classification_ogb_original.py) on a molhiv-shaped batch (README.md:121 recipe,
+    reduced width/depth): eval forward, and a training step's loss + gradients (dropout 0)."""
+    from oracle import ref_import
+    warnings.filterwarnings('ignore')
+    M = ref_import.models()
+    g = torch.Generator().manual_seed(77)
+    L, d, dh = 3, 32, 64
+    out = {}
+    # residual=True cannot be differentiated in the reference under torch 2.x (`x += x_interm[-1]` is an in-place
+    # update of a ReLU output, models_graph_classification_ogb_original.py:247) -> eval-only golden for it
+    for name, scope, vn, residual, do_train in (('ogb_local_vn', 'local', True, False, True),
+                                               ('ogb_global', 'global', False, False, True),
+                                               ('ogb_global_vn_res_eval', 'global', True, True, False)):
+        args = dict(seed=0, model_name='GSN_edge_sparse_ogb', readout='mean', dropout_features=[0.0] * (L + 1),
+                    bn=[True] * L, final_projection=[False] * L + [True], residual=residual, inject_ids=False,
+                    inject_edge_features=True, vn=vn, vn_pooling='sum', input_vn_encoder='embedding',
+                    d_out_vn_encoder=d, d_out_vn=[d] * (L - 1), id_scope=scope, d_msg=[d] * L, d_out=[d] * L,
+                    d_h=[[dh]] * L, aggr='add', flow='source_to_target', msg_kind='ogb', train_eps=[False] * L,
+                    activation_mlp='relu', bn_mlp=True, jk_mlp=False, degree_embedding='one_hot_encoder',
+                    degree_as_tag=[False] * L, retain_features=[False] + [True] * (L - 1), multi_embedding_aggr='sum',
+                    features_scope='full', input_node_encoder='atom_encoder', d_out_node_encoder=d,
+                    edge_encoder='bond_encoder', d_out_edge_encoder=[d] * L, id_embedding='embedding',
+                    d_out_id_embedding=d, d_out_degree_embedding=d, extend_dims=True, activation='relu')
+        d_in_id = [4, 6, 3]
+        ctor = dict(in_features=9, out_features=1, encoder_ids=None, d_in_id=d_in_id, in_edge_features=3,
+                    d_in_node_encoder=None, d_in_edge_encoder=None, encoder_degrees=None, d_degree=None)
+        torch.manual_seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = M['GNN_OGB'](**ctor, **args)
+        randomize(model, g)
+        if vn:      # the vn embedding is zero-initialised; make it non-trivial
+            for p in model.vn_encoder.parameters():
+                p.data.normal_(0, 0.3, generator=g)
+        ei, batch, n = rand_graph(g, n_graphs=7, lo=3, hi=9, sort=False)
+        E = ei.shape[1]
+        rows = E if scope == 'local' else n
+        atom, bond = [119, 4, 12, 12, 10, 6, 6, 2, 2], [5, 6, 2]
+        data = {'edge_index': ei, 'batch': batch,
+                'x': torch.stack([torch.randint(0, a, (n,), generator=g) for a in atom], 1),
+                'edge_features': torch.stack([torch.randint(0, b, (E,), generator=g) for b in bond], 1),
+                'identifiers': torch.stack([torch.randint(0, k, (rows,), generator=g) for k in d_in_id], 1),
+                'degrees': torch.randint(0, 5, (n,), generator=g)}
+
+        class Obj:
+            pass
+        dobj = Obj()
+        for k, v in data.items():
+            setattr(dobj, k, v)
+        model.eval()
+        with torch.no_grad():
+            y_eval = model(dobj)
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        out[name] = {'ctor': ctor, 'args': args, 'data': data, 'state_dict': sd, 'y_eval': y_eval}
+        if do_train:
+            model.train()
+            target = torch.randint(0, 2, (7, 1), generator=g).float()
+            y_train = model(dobj)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(y_train, target)
+            loss.backward()
+            grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+            out[name].update(y_train=y_train.detach(), target=target, loss=loss.detach(), grads=grads)
+            print(name, 'eval', y_eval.flatten()[:3].tolist(), 'loss', float(loss), 'n grads', len(grads))
+        else:
+            print(name, 'eval', y_eval.flatten()[:3].tolist())
+    torch.save(out, os.path.join(out_dir, 'mp_ogb.pt'))
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'ogb':
+    make_ogb(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden'))
