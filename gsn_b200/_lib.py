@@ -39,14 +39,14 @@ _SIGNATURES = {
     'gsn_mp_ogb_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     'gsn_mp_segment_sum': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp]),
     'gsn_mp_general_edge_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
-    'gsn_mp_general_edge_idx_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
+    'gsn_mp_general_edge_idx_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     'gsn_linear_fwd': (ctypes.c_int, [_vp, _vp]),
     'gsn_split_tf32': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'gsn_tc_linear_workspace_bytes': (ctypes.c_int, [_i64, _i32, _szp]),
     'gsn_tc_linear_fwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     'gsn_tc_debug_buffer': (ctypes.c_int, [_vp]),
     'gsn_pool_ptr': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
-    'gsn_encode_rows': (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    'gsn_encode_rows': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -207,7 +207,9 @@ class FusedForward:
                 efi = data.edge_features if data.edge_features.dim() == 2 else data.edge_features.unsqueeze(-1)
                 edge_cols.append((efi[:, 0], None, L['Te_off_ef']))
             node_rows = ops.encode_rows(node_cols, vcat, N, dev) if node_cols else None
-            edge_rows = ops.encode_rows(edge_cols, vcat, E, dev) if edge_cols else None
+            # edge rows are produced directly in CSR order (perm = plan.eid): the message kernel then reads them
+            # sequentially instead of chasing eid -> row
+            edge_rows = ops.encode_rows(edge_cols, vcat, E, dev, perm=plan.eid) if edge_cols else None
             # ---- dense parts
             P = ops.linear(x, L['Wp']) if L['Wp'] is not None else None
             Q = None
@@ -215,7 +217,8 @@ class FusedForward:
                 ee = m.edge_encoder[i if m.inject_edge_features else 0]
                 Q = ops.linear(ee(data.edge_features).contiguous(), L['Wq_ef'])
             S = ops.general_edge_idx(plan, dh, P=P, Q=Q, node_rows=node_rows, Tn=L['Tn'], edge_rows=edge_rows,
-                                     Te=L['Te'], scale=L['scale'], shift=L['shift'], activation=L['act_mlp'])
+                                     Te=L['Te'], scale=L['scale'], shift=L['shift'], activation=L['act_mlp'],
+                                     edge_rows_csr=True)
             # ---- update_fn (first Linear carries the folded second message Linear) + BN + act
             if L['x_cat']:
                 H = ops.linear(S, L['Wu'], bias=L['c1'], row_scale=plan.degree(), row_vec=L['vf'],

@@ -303,9 +303,10 @@ def pool_ptr(x, node_ptr, mean=False):
     return out
 
 
-def encode_rows(columns, vocab, num_rows, device):
+def encode_rows(columns, vocab, num_rows, device, perm=None):
     """columns: list of (int64 tensor view [R] (any stride), (vocab_begin, vocab_end) or None, table_off).
-    Returns int32 [R, len(columns)] rows into a concatenated embedding table."""
+    Returns int32 [R, len(columns)] rows into a concatenated embedding table; with perm (int32 [R], e.g.
+    EdgePlan.eid) output row r encodes source row perm[r]."""
     cols = (GsnEncodeCol * len(columns))()
     for i, (src, vr, off) in enumerate(columns):
         if src.dtype != torch.int64:
@@ -316,19 +317,21 @@ def encode_rows(columns, vocab, num_rows, device):
     out = torch.empty((num_rows, len(columns)), dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         _lib.call('encode_rows', 'gsn_encode_rows', ctypes.cast(cols, ctypes.c_void_p), len(columns), _lib.ptr(vocab),
-                  num_rows, _lib.ptr(out), _lib.stream_ptr())
+                  _lib.ptr(perm), num_rows, _lib.ptr(out), _lib.stream_ptr())
     return out
 
 
 def general_edge_idx(plan, dh, P=None, Q=None, node_rows=None, Tn=None, edge_rows=None, Te=None, scale=None, shift=None,
-                     activation='relu'):
+                     activation='relu', edge_rows_csr=False):
     """S[i] = sum_e act((P_i + P_j + sum Tn[node rows] + Q_e + sum Te[edge rows]) * scale + shift)"""
     S = torch.empty((plan.N, dh), dtype=torch.float32, device=plan.device)
     with torch.cuda.device(plan.device):
         _lib.call('general_edge', 'gsn_mp_general_edge_idx_fwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid),
                   _lib.ptr(plan.nbr), plan.N, plan.E, _lib.ptr(P), _lib.ptr(Q), _lib.ptr(node_rows),
                   0 if node_rows is None else node_rows.shape[1], _lib.ptr(Tn), _lib.ptr(edge_rows),
-                  0 if edge_rows is None else edge_rows.shape[1], _lib.ptr(Te), dh, _lib.ptr(scale), _lib.ptr(shift),
+                  0 if edge_rows is None else edge_rows.shape[1], _lib.ptr(Te), 0 if Te is None else Te.shape[0],
+                  int(bool(edge_rows_csr)), dh,
+                  _lib.ptr(scale), _lib.ptr(shift),
                   ACTIVATIONS[activation], _lib.ptr(S), _lib.stream_ptr())
     return S
 

@@ -278,8 +278,8 @@ typedef struct GsnEncodeCol {
 } GsnEncodeCol;
 
 #define GSN_MAX_ENCODE_COLS 16
-int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d_vocab, int64_t R, int32_t *d_out,
-                    void *stream);
+int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d_vocab, const int32_t *d_perm, int64_t R,
+                    int32_t *d_out, void *stream);   /* d_perm (optional): out row r encodes source row d_perm[r] */
 
 /*
  * 'general' message kind with categorical inputs kept as indices (layer 0 of the ZINC /
@@ -293,8 +293,11 @@ int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d
 int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
                                 int64_t E, const float *d_P, const float *d_Q, const int32_t *d_node_rows,
                                 int32_t n_node_cols, const float *d_Tn, const int32_t *d_edge_rows, int32_t n_edge_cols,
-                                const float *d_Te, int32_t dh, const float *d_scale, const float *d_shift, int32_t act,
-                                float *d_S, void *stream);
+                                const float *d_Te, int32_t te_rows, int32_t edge_rows_csr, int32_t dh, const float *d_scale,
+                                const float *d_shift, int32_t act, float *d_S, void *stream);
+/* te_rows: number of rows of d_Te (<= 4 rows with a single edge column selects a register-resident variant).
+ * edge_rows_csr = 1: d_edge_rows is ordered like d_eid (row k belongs to CSR position k; gsn_encode_rows with
+ * d_perm = d_eid), which removes one dependent load per edge; 0: indexed by edge_index column. */
 
 /* ------------------------------------------------------------------ */
 /* misc                                                                */

@@ -64,6 +64,9 @@ def test_pool_ptr_and_encode_rows():
     extra = torch.randint(0, 4, (1000,), generator=g).cuda()
     rows = ops.encode_rows([(ids_c[:, 0], ptrs[0], 0), (ids_c[:, 1], ptrs[1], 100), (ids_c[:, 2], ptrs[2], 200),
                             (extra, None, 300)], vcat, 1000, ids_c.device).cpu()
+    perm = torch.randperm(1000, generator=g).to(torch.int32)
+    rows_p = ops.encode_rows([(ids_c[:, 0], ptrs[0], 0), (extra, None, 300)], vcat, 1000, ids_c.device, perm=perm.cuda()).cpu()
+    assert torch.equal(rows_p, rows[perm.long()][:, [0, 3]])
     for c in range(3):
         exp = torch.bucketize(ids[:, c], vocab[c]) + 100 * c
         assert torch.equal(rows[:, c].long(), exp)
