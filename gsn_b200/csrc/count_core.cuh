@@ -110,6 +110,21 @@ struct VSet {
     }
 };
 
+// Work splitting for small batches: keep the elements of `s` whose ordinal inside the set is congruent to
+// `part` modulo `parts` (the sub-items of one directed edge partition its third-level candidates).
+template <int W>
+GSN_HD void keep_part(VSet<W> &s, int part, int parts) {
+    if (parts <= 1) return;
+    VSet<W> in = s;
+    s.clear();
+    int ord = 0;
+    while (!in.empty()) {
+        int v = in.pop_lowest();
+        if (ord % parts == part) s.set_bit(v);
+        ++ord;
+    }
+}
+
 // number of neighbours of the row `p` (W words) with id < b  == position of b
 // in the ascending neighbour list == slot offset inside the row
 template <int W>
@@ -188,9 +203,10 @@ GSN_HD void candidates(const GsnPlan &P, const GraphView<W> &G, const int *f, in
 // Sub-totals are pushed up the search stack so each search node costs O(1)
 // accumulator updates.
 template <int W, class Acc>
-GSN_HD void enumerate_generic(const GsnPlan &P, const GraphView<W> &G, int a, int b, Acc &acc) {
+GSN_HD void enumerate_generic(const GsnPlan &P, const GraphView<W> &G, int a, int b, Acc &acc, int part = 0, int parts = 1) {
     const int k = P.k;
     if ((P.gt_mask[1] & 1u) && !(a < b)) return;
+    if (k == 2 && part != 0) return;
     int f[GSN_MAXK];
     uint32_t cnt[GSN_MAXK];
     VSet<W> cand[GSN_MAXK];
@@ -202,6 +218,7 @@ GSN_HD void enumerate_generic(const GsnPlan &P, const GraphView<W> &G, int a, in
     } else {
         int p = 2;
         candidates<W>(P, G, f, 2, cand[2]);
+        keep_part<W>(cand[2], part, parts);
         while (true) {
             if (cand[p].empty()) {
                 if (p == 2) break;
@@ -259,7 +276,8 @@ GSN_HD void record_cycle_set(int scope, const GraphView<W> &G, const int *f, int
 }
 
 template <int W, class Acc>
-GSN_HD void enumerate_cycles(int kmin, int kmax, int induced, int scope, const GraphView<W> &G, int a, int b, Acc &acc) {
+GSN_HD void enumerate_cycles(int kmin, int kmax, int induced, int scope, const GraphView<W> &G, int a, int b, Acc &acc,
+                             int part = 0, int parts = 1) {
     if (b <= a) return;
     int f[GSN_MAXK];
     VSet<W> cand[GSN_MAXK];   // cand[p]: remaining choices for f[p]
@@ -280,7 +298,7 @@ GSN_HD void enumerate_cycles(int kmin, int kmax, int induced, int scope, const G
         ext.keep_gt(a);
         if (induced) ext.andnot_set(forb[p]);
         const int len = p + 2;
-        if (len >= kmin) {
+        if (len >= kmin && (p > 1 || part == 0)) {          // triangles on (a,b) are recorded by sub-item 0 only
             VSet<W> closers = ext;
             closers.and_with(G.row(a));
             closers.keep_gt(b);
@@ -293,6 +311,7 @@ GSN_HD void enumerate_cycles(int kmin, int kmax, int induced, int scope, const G
                 forb[p + 1].or_with(G.row(f[p]));
             }
             cand[p + 1] = ext;
+            if (p == 1) keep_part<W>(cand[2], part, parts);
             ++p;
         }
         while (p >= 2 && cand[p].empty()) --p;
@@ -307,7 +326,8 @@ GSN_HD void enumerate_cycles(int kmin, int kmax, int induced, int scope, const G
 // All clique sizes kmin..kmax in one traversal over increasing vertex tuples
 // (one representative of the k! maps).  column = size - kmin.
 template <int W, class Acc>
-GSN_HD void enumerate_cliques(int kmin, int kmax, int scope, const GraphView<W> &G, int a, int b, Acc &acc) {
+GSN_HD void enumerate_cliques(int kmin, int kmax, int scope, const GraphView<W> &G, int a, int b, Acc &acc,
+                              int part = 0, int parts = 1) {
     if (b <= a) return;
     int f[GSN_MAXK];
     VSet<W> cand[GSN_MAXK];
@@ -316,6 +336,8 @@ GSN_HD void enumerate_cliques(int kmin, int kmax, int scope, const GraphView<W> 
     cand[2].load(G.row(a));
     cand[2].and_with(G.row(b));
     cand[2].keep_gt(b);
+    const VSet<W> pool2 = cand[2];           // every common neighbour > b: the pool deeper levels draw from
+    keep_part<W>(cand[2], part, parts);      // each sub-item records and extends its own share of the triangles
     int p = 2;
     bool fresh = true;   // cand[p] was just computed: record the (p+1)-cliques it closes
     while (true) {
@@ -355,7 +377,12 @@ GSN_HD void enumerate_cliques(int kmin, int kmax, int scope, const GraphView<W> 
         }
         int j = cand[p].pop_lowest();
         f[p] = j;
-        cand[p + 1] = cand[p];          // remaining candidates are all > j already (ascending pop)
+        if (p == 2) {                   // the sub-item filter applies to the choice of f[2] only
+            cand[3] = pool2;
+            cand[3].keep_gt(j);
+        } else {
+            cand[p + 1] = cand[p];      // remaining candidates are all > j already (ascending pop)
+        }
         cand[p + 1].and_with(G.row(j));
         ++p;
         fresh = true;

@@ -34,6 +34,7 @@ struct CountParams {
     int32_t smem_adj_words;  // capacity of the adjacency stage (uint64 words), 0 = read HBM
     int32_t smem_row_words;  // capacity of the rowptr stage (int32)
     int32_t smem_acc_words;  // capacity of the accumulator stage (uint32)
+    int32_t parts;           // sub-items per directed edge (small batches: shorter critical path)
     int64_t *out;            // vertex scope: [N, out_ld] ; edge scope: unused here
     int64_t out_ld;
     uint32_t *slot_acc;      // edge scope: [S, n_cols]
@@ -62,10 +63,10 @@ struct GlobalAcc {
 };
 
 template <int W, class Acc>
-__device__ __forceinline__ void run_item(const GsnPlan &P, const GraphView<W> &G, int a, int b, Acc &acc) {
-    if (P.family == GSN_FAMILY_CYCLES) enumerate_cycles<W>(P.kmin, P.kmax, P.induced, P.scope, G, a, b, acc);
-    else if (P.family == GSN_FAMILY_CLIQUES) enumerate_cliques<W>(P.kmin, P.kmax, P.scope, G, a, b, acc);
-    else enumerate_generic<W>(P, G, a, b, acc);
+__device__ __forceinline__ void run_item(const GsnPlan &P, const GraphView<W> &G, int a, int b, Acc &acc, int part, int parts) {
+    if (P.family == GSN_FAMILY_CYCLES) enumerate_cycles<W>(P.kmin, P.kmax, P.induced, P.scope, G, a, b, acc, part, parts);
+    else if (P.family == GSN_FAMILY_CLIQUES) enumerate_cliques<W>(P.kmin, P.kmax, P.scope, G, a, b, acc, part, parts);
+    else enumerate_generic<W>(P, G, a, b, acc, part, parts);
 }
 
 __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t n, int64_t key) {
@@ -148,20 +149,22 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
     const uint64_t *adj_base = stage ? sm_adj + (v0 * W - aw0) : prm.adj + v0 * W;       // row of node v0
     const int32_t *row_base = stage ? sm_row + (v0 - rw0) : prm.rowptr + v0;             // rowptr of node v0
 
+    const int parts = prm.parts;
     while (true) {
         int it = atomicAdd(&ticket, 1);
-        if (it >= ns) break;
-        const int s = s0 + it;
+        if (it >= ns * parts) break;
+        const int s = s0 + it / parts;
+        const int part = it % parts;
         const int a = prm.slot_src[s], b = prm.slot_dst[s];
         const int gb = prm.nbase[a];                      // first node of the graph
         const int off = (int)(gb - v0);
         GraphView<W> G{adj_base + (size_t)off * W, row_base + off};
         if (acc_in_smem) {
             SmemAcc acc{sm_acc, C, off, s0};
-            run_item<W>(P, G, a - gb, b - gb, acc);
+            run_item<W>(P, G, a - gb, b - gb, acc, part, parts);
         } else {
             GlobalAcc acc{(unsigned long long *)(prm.out + P.col0), prm.out_ld, (int64_t)gb, prm.slot_acc, C};
-            run_item<W>(P, G, a - gb, b - gb, acc);
+            run_item<W>(P, G, a - gb, b - gb, acc, part, parts);
         }
     }
     if (!acc_in_smem) return;
@@ -289,6 +292,8 @@ extern "C" int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t
     int64_t left = budget - adj_words * 8 - row_words * 4;
     if (acc_words * 4 > left) acc_words = left / 4;
     prm.T = (int32_t)T;
+    // few items (small batch): split every directed edge into sub-items so that more threads share the search
+    prm.parts = E < (int64_t)kNumSMs * 512 ? 4 : (E < (int64_t)kNumSMs * 2048 ? 2 : 1);
     prm.smem_adj_words = (int32_t)adj_words;
     prm.smem_row_words = (int32_t)row_words;
     prm.smem_acc_words = (int32_t)acc_words;

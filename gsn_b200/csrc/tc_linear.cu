@@ -68,16 +68,20 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, int STAGES>
+// SPLIT_IN_KERNEL = false: tmA_hi / tmA_lo address pre-split activations (split_a_kernel).
+// SPLIT_IN_KERNEL = true : tmA_hi / tmA_lo are the RAW fp32 sources A1 [M,K1] and A2 [M,K2] (K1 % 32 == 0 when K2 > 0);
+//                          warps 4-7 split every landed tile in shared memory (hi in place, lo next to it) while the
+//                          previous stage is being multiplied: no extra kernel, no extra HBM traffic.
+template <int BN, int STAGES, bool SPLIT_IN_KERNEL>
 __global__ void __launch_bounds__(256, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                 const __grid_constant__ TcEpilogue ep) {
+                 const __grid_constant__ TcEpilogue ep, int K1) {
     constexpr int A_TILE = TC_BM * TC_BK * 4;      // bytes
     constexpr int W_TILE = BN * TC_BK * 4;
     constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], conv_bar[STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
     const long long t_begin = clock64();
@@ -98,6 +102,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&conv_bar[s], 4);          // one arrival per converter warp
         }
         mbar_init(&tmem_full_bar, 1);
         mbar_fence_init();
@@ -122,10 +127,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint32_t ph = (kt / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             unsigned char *st = ring + (size_t)s * STAGE;
-            mbar_arrive_expect_tx(&full_bar[s], STAGE);
             const int k0 = kt * TC_BK;
-            tma_load_2d(st, &tmA_hi, k0, m0, &full_bar[s]);
-            tma_load_2d(st + A_TILE, &tmA_lo, k0, m0, &full_bar[s]);
+            if (SPLIT_IN_KERNEL) {
+                mbar_arrive_expect_tx(&full_bar[s], A_TILE + 2 * W_TILE);
+                if (k0 < K1) tma_load_2d(st, &tmA_hi, k0, m0, &full_bar[s]);           // raw A1 tile
+                else tma_load_2d(st, &tmA_lo, k0 - K1, m0, &full_bar[s]);             // raw A2 tile
+            } else {
+                mbar_arrive_expect_tx(&full_bar[s], STAGE);
+                tma_load_2d(st, &tmA_hi, k0, m0, &full_bar[s]);
+                tma_load_2d(st + A_TILE, &tmA_lo, k0, m0, &full_bar[s]);
+            }
             tma_load_2d(st + 2 * A_TILE, &tmW_hi, k0, n0, &full_bar[s]);
             tma_load_2d(st + 2 * A_TILE + W_TILE, &tmW_lo, k0, n0, &full_bar[s]);
         }
@@ -137,7 +148,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int kt = 0; kt < nk; ++kt) {
             const int s = kt % STAGES;
             const uint32_t ph = (kt / STAGES) & 1;
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait(SPLIT_IN_KERNEL ? &conv_bar[s] : &full_bar[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             unsigned char *st = ring + (size_t)s * STAGE;
             const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + A_TILE);
@@ -157,6 +168,37 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         umma_commit(&tmem_full_bar);             // accumulator complete
         if (dbg) dbg[3] = clock64();
+    } else if (SPLIT_IN_KERNEL && warp >= 4) {
+        // ---------------- converters: raw fp32 tile -> (hi, lo) tf32 pair, elementwise in the swizzled layout
+        const int tid = threadIdx.x - 128;
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            float4 *hi = reinterpret_cast<float4 *>(ring + (size_t)s * STAGE);
+            float4 *lo = reinterpret_cast<float4 *>(ring + (size_t)s * STAGE + A_TILE);
+#pragma unroll
+            for (int i = 0; i < A_TILE / 16 / 128; ++i) {
+                float4 a = hi[tid + i * 128], h, l;
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.x)); h.x = __uint_as_float(u);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.y)); h.y = __uint_as_float(u);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.z)); h.z = __uint_as_float(u);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.w)); h.w = __uint_as_float(u);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.x - h.x)); l.x = __uint_as_float(u);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.y - h.y)); l.y = __uint_as_float(u);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.z - h.z)); l.z = __uint_as_float(u);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.w - h.w)); l.w = __uint_as_float(u);
+                hi[tid + i * 128] = h;
+                lo[tid + i * 128] = l;
+            }
+            // generic-proxy writes must be visible to the tensor core (async proxy) before the MMA is issued
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
+            }
+        }
     }
     __syncwarp();
     {
@@ -293,6 +335,7 @@ __global__ void split_a_kernel(const float *__restrict__ A1, int K1, int lda1, c
 }
 
 void *g_tc_debug = nullptr;
+bool g_tc_force_presplit = false;     // testing aid: exercise the split_a_kernel path
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -328,17 +371,17 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t c
     return GSN_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT>
 static int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &w_hi, const CUtensorMap &w_lo,
-                     const TcEpilogue &ep, cudaStream_t stream) {
+                     const TcEpilogue &ep, int K1, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024;
     static bool attr = false;
     if (!attr) {
-        GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     dim3 grid((unsigned)ceil_div(ep.M, TC_BM), (unsigned)ceil_div(ep.Nout, BN));
-    tc_linear_kernel<BN, STAGES><<<grid, 256, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, ep);
+    tc_linear_kernel<BN, STAGES, SPLIT><<<grid, 256, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, ep, K1);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("tc_linear_kernel");
     return GSN_OK;
@@ -367,7 +410,7 @@ extern "C" int gsn_tc_linear_workspace_bytes(int64_t M, int32_t K, size_t *bytes
 
 extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const float *d_Wlo, void *d_ws, size_t ws_bytes,
                                  void *stream_) {
-    if (!h_p || !d_Whi || !d_Wlo || !d_ws) return GSN_E_INVALID;
+    if (!h_p || !d_Whi || !d_Wlo) return GSN_E_INVALID;
     const GsnLinear &p = *h_p;
     const int K = p.K1 + p.K2;
     if (p.M < 0 || p.Nout < 1 || K < 4 || !p.C || !p.A1) return GSN_E_INVALID;
@@ -377,28 +420,39 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
         return GSN_E_UNSUPPORTED;
     if ((p.row_scale == nullptr) != (p.row_vec == nullptr) || (p.tab == nullptr) != (p.tab_idx == nullptr)) return GSN_E_INVALID;
     if (p.M == 0) return GSN_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int BN = p.Nout > 128 ? 256 : (p.Nout > 64 ? 128 : 64);
+    TcEpilogue ep{p.bias, p.row_scale, p.row_vec, p.tab, p.scale, p.shift, p.tab_idx, p.C,
+                  p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate, (long long *)g_tc_debug};
+    CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
+    int rc;
+    if ((rc = make_map(&mW_hi, d_Whi, p.Nout, K, K, BN))) return rc;
+    if ((rc = make_map(&mW_lo, d_Wlo, p.Nout, K, K, BN))) return rc;
+    const bool split_in_kernel = (p.K2 == 0 || p.K1 % TC_BK == 0) && !g_tc_force_presplit;
+    if (split_in_kernel) {
+        // raw activations straight through TMA; the tile is split into (hi, lo) in shared memory by the kernel
+        if ((rc = make_map(&mA_hi, p.A1, p.M, p.K1, p.lda1, TC_BM))) return rc;
+        if (p.K2 > 0) { if ((rc = make_map(&mA_lo, p.A2, p.M, p.K2, p.lda2, TC_BM))) return rc; }
+        else mA_lo = mA_hi;
+        if (BN == 256) return launch_tc<256, 2, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
+        if (BN == 128) return launch_tc<128, 3, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
+        return launch_tc<64, 4, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
+    }
     size_t need = 0;
     gsn_tc_linear_workspace_bytes(p.M, K, &need);
-    if (ws_bytes < need) return GSN_E_WORKSPACE;
-    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_ws || ws_bytes < need) return GSN_E_WORKSPACE;
     float *a_hi = (float *)(((uintptr_t)d_ws + 1023) & ~(uintptr_t)1023);
     float *a_lo = a_hi + align_up(sizeof(float) * (size_t)p.M * K, 1024) / sizeof(float);
     const int64_t n4 = (int64_t)p.M * (K / 4);
     split_a_kernel<<<(unsigned)ceil_div(n4, 256), 256, 0, stream>>>(p.A1, p.K1, p.lda1, p.A2, p.K2, p.lda2, p.M, a_hi, a_lo);
     GSN_BUMP(1);
-    const int BN = p.Nout > 128 ? 256 : (p.Nout > 64 ? 128 : 64);
-    CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
-    int rc;
     if ((rc = make_map(&mA_hi, a_hi, p.M, K, K, TC_BM))) return rc;
     if ((rc = make_map(&mA_lo, a_lo, p.M, K, K, TC_BM))) return rc;
-    if ((rc = make_map(&mW_hi, d_Whi, p.Nout, K, K, BN))) return rc;
-    if ((rc = make_map(&mW_lo, d_Wlo, p.Nout, K, K, BN))) return rc;
-    TcEpilogue ep{p.bias, p.row_scale, p.row_vec, p.tab, p.scale, p.shift, p.tab_idx, p.C,
-                  p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate, (long long *)g_tc_debug};
-    if (BN == 256) return launch_tc<256, 2>(mA_hi, mA_lo, mW_hi, mW_lo, ep, stream);
-    if (BN == 128) return launch_tc<128, 3>(mA_hi, mA_lo, mW_hi, mW_lo, ep, stream);
-    return launch_tc<64, 4>(mA_hi, mA_lo, mW_hi, mW_lo, ep, stream);
+    if (BN == 256) return launch_tc<256, 2, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
+    if (BN == 128) return launch_tc<128, 3, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
+    return launch_tc<64, 4, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
 }
 
 // profiling aid: when set, every tc_linear CTA writes 8 clock64 stamps to d_buf[cta*8 ..]
 extern "C" int gsn_tc_debug_buffer(void *d_buf) { gsn::g_tc_debug = d_buf; return GSN_OK; }
+extern "C" int gsn_tc_force_presplit(int on) { gsn::g_tc_force_presplit = on != 0; return GSN_OK; }

@@ -225,6 +225,7 @@ def _dp(t):
 
 # Tensor-core dense tail (tcgen05 3xTF32).  "auto": use it whenever the shapes allow (K % 4 == 0, aligned).
 TENSOR_CORES = 'auto'       # 'auto' | 'off'
+FORCE_PRESPLIT = False       # testing aid (see gsn_tc_force_presplit)
 _wsplit_cache = {}
 
 
@@ -282,11 +283,13 @@ def linear(A1, W, bias=None, A2=None, row_scale=None, row_vec=None, tab_idx=None
     with torch.cuda.device(dev):
         if _tc_eligible(A1, A2, W):
             whi, wlo = split_weight(W)
-            nb = ctypes.c_size_t(0)
-            _lib.check(_lib.lib().gsn_tc_linear_workspace_bytes(M, p.K1 + p.K2, ctypes.byref(nb)), 'gsn_tc_linear_workspace_bytes')
-            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            ws, nbytes = None, 0
+            if FORCE_PRESPLIT or (p.K2 > 0 and p.K1 % 32 != 0):       # only then the activations need a pre-pass
+                nb = ctypes.c_size_t(0)
+                _lib.check(_lib.lib().gsn_tc_linear_workspace_bytes(M, p.K1 + p.K2, ctypes.byref(nb)), 'gsn_tc_linear_workspace_bytes')
+                ws, nbytes = torch.empty(nb.value, dtype=torch.uint8, device=dev), nb.value
             _lib.call('tc_linear', 'gsn_tc_linear_fwd', ctypes.byref(p), _lib.ptr(whi), _lib.ptr(wlo), _lib.ptr(ws),
-                      nb.value, _lib.stream_ptr())
+                      nbytes, _lib.stream_ptr())
         else:
             _lib.call('linear', 'gsn_linear_fwd', ctypes.byref(p), _lib.stream_ptr())
     return out

@@ -243,8 +243,9 @@ int gsn_linear_fwd(const GsnLinear *h_p, void *stream);
  * fp32-equivalent accuracy through 3xTF32 (a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi).
  *   gsn_split_tf32           x -> (rn_tf32(x), x - rn_tf32(x)), [rows, cols] with row stride ld -> dense [rows, cols];
  *                            used once per weight matrix (W in nn.Linear layout [Nout, K1+K2])
- *   gsn_tc_linear_fwd        same meaning as gsn_linear_fwd; d_Whi / d_Wlo are the split weights; d_ws holds the
- *                            split activations (gsn_tc_linear_workspace_bytes).  Needs K1, K2, lda1, lda2 % 4 == 0
+ *   gsn_tc_linear_fwd        same meaning as gsn_linear_fwd; d_Whi / d_Wlo are the split weights.  Activations are
+ *                            split inside the kernel (shared memory) when K2 == 0 or K1 % 32 == 0; otherwise by a
+ *                            small pre-pass into d_ws (gsn_tc_linear_workspace_bytes; d_ws may be NULL otherwise).  Needs K1, K2, lda1, lda2 % 4 == 0
  *                            and 16-byte aligned operands, otherwise GSN_E_UNSUPPORTED (use gsn_linear_fwd).
  */
 int gsn_split_tf32(const float *d_src, int64_t rows, int32_t cols, int32_t ld, float *d_hi, float *d_lo, void *stream);
@@ -253,6 +254,8 @@ int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const float *d_W
                       void *stream);
 /* Profiling aid: non-NULL -> every tc_linear CTA writes 8 clock64 stamps to d_buf[cta*8..]; NULL disables. */
 int gsn_tc_debug_buffer(void *d_buf);
+/* Testing aid: 1 forces the pre-split path (split_a_kernel + workspace) even when the in-kernel split applies. */
+int gsn_tc_force_presplit(int on);
 
 /*
  * out[g,:] = sum (mean=1: average) of the rows x[ptr[g] .. ptr[g+1]) : the readouts

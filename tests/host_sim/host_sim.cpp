@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../gsn_b200/csrc/count_core.cuh"
 
+static int g_parts = 1;
 namespace {
 struct HostAcc {
     int64_t *v;      // [n, ld]
@@ -43,12 +44,14 @@ int run(int n, int64_t E, const int64_t *src, const int64_t *dst, const GsnPlan 
         row.load(G.row(a));
         while (!row.empty()) {
             int b = row.pop_lowest();
-            if (P->family == GSN_FAMILY_CYCLES)
-                gsn::enumerate_cycles<W>(P->kmin, P->kmax, P->induced, P->scope, G, a, b, acc);
-            else if (P->family == GSN_FAMILY_CLIQUES)
-                gsn::enumerate_cliques<W>(P->kmin, P->kmax, P->scope, G, a, b, acc);
-            else
-                gsn::enumerate_generic<W>(*P, G, a, b, acc);
+            for (int part = 0; part < g_parts; ++part) {
+                if (P->family == GSN_FAMILY_CYCLES)
+                    gsn::enumerate_cycles<W>(P->kmin, P->kmax, P->induced, P->scope, G, a, b, acc, part, g_parts);
+                else if (P->family == GSN_FAMILY_CLIQUES)
+                    gsn::enumerate_cliques<W>(P->kmin, P->kmax, P->scope, G, a, b, acc, part, g_parts);
+                else
+                    gsn::enumerate_generic<W>(*P, G, a, b, acc, part, g_parts);
+            }
         }
     }
     if (P->scope == 0) {
@@ -75,6 +78,8 @@ int run(int n, int64_t E, const int64_t *src, const int64_t *dst, const GsnPlan 
     return missing ? -1 : 0;
 }
 }  // namespace
+
+extern "C" void gsn_host_sim_set_parts(int parts) { g_parts = parts < 1 ? 1 : parts; }
 
 extern "C" int gsn_host_sim_count(int n, int64_t E, const int64_t *src, const int64_t *dst, const GsnPlan *P,
                                   int64_t *out, int ld) {

@@ -24,7 +24,8 @@ def host_sim():
     L = ctypes.CDLL(so)
     i64p = ctypes.POINTER(ctypes.c_int64)
 
-    def run(ei, n, plans, rows, ld):
+    def run(ei, n, plans, rows, ld, parts=1):
+        L.gsn_host_sim_set_parts(parts)
         ei = np.ascontiguousarray(ei, dtype=np.int64)
         src_, dst_ = np.ascontiguousarray(ei[0]), np.ascontiguousarray(ei[1])
         o = np.zeros((rows, ld), dtype=np.int64)
@@ -117,6 +118,7 @@ def test_enumeration_cores_vs_oracle(host_sim, family, scope_name, induced, grap
             if ei.shape[1] == 0:
                 continue
             rows = n if scope == 0 else ei.shape[1]
-            got = host_sim(ei, n, plans, rows, ld)
             exp = np.concatenate([count_c.count_graph(ei, sd, induced, n, scope) for sd in osds], 1).astype(np.int64)
-            assert np.array_equal(got, exp), (family, scope_name, induced, fuse, n)
+            for parts in (1, 4):        # sub-items per directed edge (small-batch work splitting)
+                got = host_sim(ei, n, plans, rows, ld, parts)
+                assert np.array_equal(got, exp), (family, scope_name, induced, fuse, n, parts)
