@@ -198,6 +198,119 @@ __global__ void k_slot_cols(const int64_t *__restrict__ src, const int64_t *__re
     atomicMax(&slot_col[slot_of_rt(adj, rowptr, W, a, lb)], (int32_t)e);
 }
 
+// Small batches: the whole graph build in ONE CTA (see csr_build_small_kernel): node bases, adjacency bits,
+// degrees + scan, slots and the edge_dict, with the adjacency words and the scan in shared memory.
+constexpr int kGraphSmallMaxWords = 8192;     // N * W adjacency words (64 KB) ...
+constexpr int kGraphSmallMaxN = 8192;         // ... and N + 1 row offsets (32 KB)
+__global__ void __launch_bounds__(1024) graph_build_small_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
+                                                                 int E, const int64_t *__restrict__ node_ptr, int G, int N, int W,
+                                                                 int32_t *__restrict__ nbase, uint64_t *__restrict__ adj,
+                                                                 int32_t *__restrict__ rowptr, int32_t *__restrict__ slot_src,
+                                                                 int32_t *__restrict__ slot_dst, int32_t *__restrict__ slot_col,
+                                                                 int32_t *status) {
+    extern __shared__ unsigned long long smg[];          // adj[N*W] | rp[N+1] (int32) | nb[N] (int32)
+    unsigned long long *sadj = smg;
+    int32_t *rp = (int32_t *)(smg + (size_t)N * W);
+    int32_t *nb = rp + (N + 1);
+    __shared__ int32_t warp_tot[32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N * W; i += 1024) sadj[i] = 0ull;
+    for (int v = tid; v < N; v += 1024) {
+        int lo = 0, hi = G;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (node_ptr[mid] <= v) lo = mid; else hi = mid;
+        }
+        const int64_t b = node_ptr[lo];
+        nb[v] = (int32_t)b;
+        nbase[v] = (int32_t)b;
+        if (v == b && node_ptr[lo + 1] - b > (int64_t)64 * W) atomicOr(status, GSN_S_GRAPH_TOO_LARGE);
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += 1024) {
+        const int64_t a = src[e], b = dst[e];
+        if (a < 0 || b < 0 || a >= N || b >= N) { atomicOr(status, GSN_S_INDEX_RANGE); continue; }
+        if (a == b) continue;
+        const int base = nb[a];
+        if (nb[b] != base) { atomicOr(status, GSN_S_CROSS_GRAPH_EDGE); continue; }
+        const int la = (int)(a - base), lb = (int)(b - base);
+        if (la >= 64 * W || lb >= 64 * W) continue;
+        atomicOr(&sadj[(size_t)a * W + (lb >> 6)], 1ull << (lb & 63));
+        atomicOr(&sadj[(size_t)b * W + (la >> 6)], 1ull << (la & 63));
+    }
+    __syncthreads();
+    // degrees -> exclusive scan (each thread owns a contiguous span of vertices)
+    const int span = (N + 1 + 1023) / 1024;
+    const int b0 = tid * span, b1 = min(b0 + span, N + 1);
+    int local = 0;
+    for (int v = b0; v < b1; ++v) {
+        int d = 0;
+        if (v < N)
+            for (int w = 0; w < W; ++w) d += __popcll(sadj[(size_t)v * W + w]);
+        rp[v] = d;
+        local += d;
+    }
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int v = warp_tot[tid], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (tid >= o) iv += t;
+        }
+        warp_tot[tid] = iv - v;
+    }
+    __syncthreads();
+    int run = warp_tot[tid >> 5] + incl - local;
+    for (int v = b0; v < b1; ++v) {
+        const int d = rp[v];
+        rp[v] = run;
+        run += d;
+    }
+    __syncthreads();
+    for (int v = tid; v <= N; v += 1024) rowptr[v] = rp[v];
+    for (int i = tid; i < N * W; i += 1024) adj[i] = sadj[i];
+    for (int v = tid; v < N; v += 1024) {
+        int s = rp[v];
+        const int base = nb[v];
+        for (int w = 0; w < W; ++w) {
+            unsigned long long x = sadj[(size_t)v * W + w];
+            while (x) {
+                const int b = __ffsll((long long)x) - 1;
+                x &= x - 1;
+                slot_src[s] = v;
+                slot_dst[s] = base + w * 64 + b;
+                slot_col[s] = -1;
+                ++s;
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += 1024) {
+        const int64_t a = src[e], b = dst[e];
+        if (a < 0 || b < 0 || a >= N || b >= N || a == b) continue;
+        const int base = nb[a];
+        if (nb[b] != base) continue;
+        const int lb = (int)(b - base);
+        if (lb >= 64 * W || a - base >= 64 * W) continue;
+        int r = 0;
+        for (int i = 0; i < W; ++i) {
+            const int lo = i * 64;
+            const unsigned long long word = sadj[(size_t)a * W + i];
+            if (lb >= lo + 64) r += __popcll(word);
+            else if (lb > lo) r += __popcll(word & ((1ull << (lb - lo)) - 1ull));
+        }
+        atomicMax(&slot_col[rp[a] + r], e);
+    }
+}
+
 }  // namespace gsn
 
 using namespace gsn;
@@ -228,6 +341,20 @@ extern "C" int gsn_graph_build(const int64_t *d_edge_index, int64_t E, const int
     int32_t *scan_tmp = (int32_t *)(ws + L.scan_tmp);
     const int64_t *src = d_edge_index, *dst = d_edge_index + E;
 
+    if (N > 0 && N <= kGraphSmallMaxN && (int64_t)N * W <= kGraphSmallMaxWords && E <= 65536) {
+        const size_t smem = sizeof(uint64_t) * (size_t)N * W + sizeof(int32_t) * (size_t)(2 * N + 2);
+        static bool attr = false;
+        if (!attr) {
+            GSN_CUDA_OK(cudaFuncSetAttribute(graph_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(uint64_t) * kGraphSmallMaxWords + sizeof(int32_t) * (2 * kGraphSmallMaxN + 2))));
+            attr = true;
+        }
+        graph_build_small_kernel<<<1, 1024, smem, stream>>>(src, dst, (int)E, d_node_ptr, (int)G, (int)N, W, nbase, adj, rowptr,
+                                                            slot_src, slot_dst, slot_col, d_status);
+        GSN_BUMP(1);
+        GSN_LAUNCH_OK("gsn_graph_build");
+        return GSN_OK;
+    }
     GSN_CUDA_OK(cudaMemsetAsync(adj, 0, sizeof(uint64_t) * ((size_t)N * W + 4), stream));
     if (N == 0) {
         GSN_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * 8, stream));

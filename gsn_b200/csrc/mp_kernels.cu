@@ -56,6 +56,78 @@ __global__ void k_sort_rows(const int32_t *__restrict__ rowptr, int64_t N, int32
     }
 }
 
+// Small batches (the B = 128 ZINC step has N ~ 3k, E ~ 6k): the whole grouping in ONE CTA -- histogram, scan,
+// fill and per-row sort through shared memory -- instead of a memset + 6 launches that are pure launch latency.
+constexpr int kCsrSmallMaxN = 12288;      // 2 * 4 * N bytes of shared memory
+__global__ void __launch_bounds__(1024) csr_build_small_kernel(const int64_t *__restrict__ key, const int64_t *__restrict__ other,
+                                                               int E, int N, int32_t *__restrict__ rowptr,
+                                                               int32_t *__restrict__ eid, int32_t *__restrict__ nbr,
+                                                               int32_t *status) {
+    extern __shared__ int32_t sm[];          // cnt[N+1] | cursor[N]
+    int32_t *cnt = sm, *cursor = sm + (N + 1);
+    __shared__ int32_t warp_tot[32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= N; i += 1024) cnt[i] = 0;
+    __syncthreads();
+    for (int e = tid; e < E; e += 1024) {
+        const int64_t k = key[e];
+        if (k < 0 || k >= N) atomicOr(status, GSN_S_INDEX_RANGE);
+        else atomicAdd(&cnt[k], 1);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..N] : each thread owns a contiguous span
+    const int span = (N + 1 + 1023) / 1024;
+    const int b0 = tid * span, b1 = min(b0 + span, N + 1);
+    int local = 0;
+    for (int i = b0; i < b1; ++i) local += cnt[i];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int v = warp_tot[tid], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (tid >= o) iv += t;
+        }
+        warp_tot[tid] = iv - v;               // exclusive offsets of the warps
+    }
+    __syncthreads();
+    int run = warp_tot[tid >> 5] + incl - local;
+    for (int i = b0; i < b1; ++i) {
+        const int c = cnt[i];
+        cnt[i] = run;                          // cnt becomes rowptr
+        if (i < N) cursor[i] = run;
+        run += c;
+    }
+    __syncthreads();
+    for (int i = tid; i <= N; i += 1024) rowptr[i] = cnt[i];
+    for (int e = tid; e < E; e += 1024) {
+        const int64_t k = key[e];
+        if (k < 0 || k >= N) continue;
+        eid[atomicAdd(&cursor[k], 1)] = e;
+    }
+    __syncthreads();
+    for (int r = tid; r < N; r += 1024) {
+        const int b = cnt[r], en = cnt[r + 1];
+        for (int i = b + 1; i < en; ++i) {
+            int v = eid[i], j = i - 1;
+            while (j >= b && eid[j] > v) { eid[j + 1] = eid[j]; --j; }
+            eid[j + 1] = v;
+        }
+        for (int i = b; i < en; ++i) {
+            int64_t o = other[eid[i]];
+            if (o < 0 || o >= N) { atomicOr(status, GSN_S_INDEX_RANGE); o = 0; }
+            nbr[i] = (int32_t)o;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ vector helpers
 template <int VEC> struct Vec;
 template <> struct Vec<1> {
@@ -448,6 +520,19 @@ extern "C" int gsn_csr_build(const int64_t *d_key, const int64_t *d_other, int64
     int32_t *cnt = (int32_t *)d_ws;
     int32_t *cursor = (int32_t *)((char *)d_ws + seg);
     int32_t *scan_tmp = (int32_t *)((char *)d_ws + 2 * seg);
+    if (N <= kCsrSmallMaxN && E <= 8 * kCsrSmallMaxN) {
+        const size_t smem = sizeof(int32_t) * (size_t)(2 * N + 2);
+        static bool attr = false;
+        if (!attr) {
+            GSN_CUDA_OK(cudaFuncSetAttribute(csr_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(int32_t) * (2 * kCsrSmallMaxN + 2))));
+            attr = true;
+        }
+        csr_build_small_kernel<<<1, 1024, smem, stream>>>(d_key, d_other, (int)E, (int)N, d_rowptr, d_eid, d_nbr, d_status);
+        GSN_BUMP(1);
+        GSN_LAUNCH_OK("gsn_csr_build");
+        return GSN_OK;
+    }
     GSN_CUDA_OK(cudaMemsetAsync(d_ws, 0, 2 * seg, stream));
     const int TB = 256;
     if (E > 0) k_hist<<<(unsigned)ceil_div(E, TB), TB, 0, stream>>>(d_key, E, N, cnt, d_status);

@@ -190,6 +190,7 @@ class FusedForward:
         if not x_cat:
             x = m.input_node_encoder(data.x)
         x_interm = [x]
+        ef_rows_cache = {}          # (offset) -> encoded edge-feature rows in CSR order, shared by the layers
         for i, (conv, L) in enumerate(zip(m.conv, self.layers)):
             plan = ops.edge_plan(edge_index, N, L['flow'])
             dh = L['dh']
@@ -209,7 +210,14 @@ class FusedForward:
             node_rows = ops.encode_rows(node_cols, vcat, N, dev) if node_cols else None
             # edge rows are produced directly in CSR order (perm = plan.eid): the message kernel then reads them
             # sequentially instead of chasing eid -> row
-            edge_rows = ops.encode_rows(edge_cols, vcat, E, dev, perm=plan.eid) if edge_cols else None
+            only_ef = len(edge_cols) == 1 and L['uses_ef'] and L['ef_cat']
+            key = (L['Te_off_ef'], L['flow'])
+            if only_ef and key in ef_rows_cache:
+                edge_rows = ef_rows_cache[key]
+            else:
+                edge_rows = ops.encode_rows(edge_cols, vcat, E, dev, perm=plan.eid) if edge_cols else None
+                if only_ef:
+                    ef_rows_cache[key] = edge_rows
             # ---- dense parts
             P = ops.linear(x, L['Wp']) if L['Wp'] is not None else None
             Q = None
