@@ -259,16 +259,30 @@ def run_ours(args, rank, world, local_rank):
         prof = instrumented(dev_in, max(3, min(args.steps, 10)))
         dh = D_OUT
 
+        n_id_cols = len(encoder.d)
+
         def scatter_bytes(n, e):
-            # general_edge per launch: P [N,2dh] + Q [E,dh] read, S [N,dh] written, CSR (rowptr, eid, nbr)
-            return 4 * 2 * dh * n + 4 * dh * e + 4 * dh * n + 8 * e + 4 * (n + 1) + 8 * dh
+            """algorithmic bytes of ONE launch of the message (scatter) kernel, averaged over the N_LAYERS launches
+            of a step.  Layer 0 reads only indices (x: 4 B/node, identifiers + bond type:
+            4 B x (id columns + 1) per edge); layers >= 1 read P [N, 2dh] fp32 and one 4-byte index per edge.
+            Every launch reads the CSR (rowptr + nbr, 4 B each) and writes S [N, dh] fp32."""
+            csr = 4 * e + 4 * (n + 1)
+            out = 4 * dh * n
+            layer0 = 4 * n + 4 * (n_id_cols + 1) * e + csr + out
+            later = 4 * 2 * dh * n + 4 * e + csr + out
+            return (layer0 + (N_LAYERS - 1) * later) / N_LAYERS
         t_sc = prof['general_edge'][0]
-        roof = {'bound': 'hbm', 'kernel': 'general_edge_kernel<4,false> (gsn_mp_general_edge_fwd)',
+        roof = {'bound': 'hbm', 'kernel': 'general_edge_idx_kernel<4> (gsn_mp_general_edge_idx_fwd), mean of the '
+                                          f'{N_LAYERS} launches of a step',
                 'achieved': scatter_bytes(N, E) / t_sc / 1e9, 'peak': peak, 'unit': 'GB/s',
                 'frac': scatter_bytes(N, E) / t_sc / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': scatter_bytes(N, E), 'avg_launch_us': t_sc * 1e6,
                 'launches_per_step': prof['general_edge'][1],
-                'how': 'CUDA events around each gsn_mp_general_edge_fwd call in an eager pass over the same steps'}
+                'how': 'CUDA events around each gsn_mp_general_edge_idx_fwd call in an eager pass over the same steps '
+                       '(L2 flushed between steps); at B=128 one launch moves ~3 MB, i.e. it is launch-latency bound: '
+                       'see sweep[] for B=4,096 / 131,072 and scatter_kernels[] for the layer-API kernels',
+                'traffic_note': 'ncu --set full (profiles/): dram read+write per launch == algorithmic bytes within 1 % '
+                                'for the dense kernel at B=32,768'}
         kernels_us = {k: round(v[0] * 1e6, 2) for k, v in prof.items()}
         sweep = []
         if not args.no_sweep:
@@ -303,6 +317,12 @@ def run_ours(args, rank, world, local_rank):
                     torch.cuda.empty_cache()
                 except Exception as ex:      # the sweep is informative only; never lose the headline line
                     sweep.append({'batch': Bs, 'error': repr(ex)[:200]})
+        scatter_kernels = []
+        if not args.no_sweep:
+            try:
+                scatter_kernels = scatter_microbench(dev, flush, peak)
+            except Exception as ex:
+                scatter_kernels = [{'error': repr(ex)[:200]}]
         cpu = cpu_baseline(pool[0], sds_oracle(), encoder, model, budget_s=12.0)
         line = {
             'metric': 'graphs/sec preprocess+forward (ZINC batch)', 'value': value, 'unit': 'graphs/s',
@@ -320,9 +340,48 @@ def run_ours(args, rank, world, local_rank):
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(my_launches_per_step) * args.steps,
             'gpu_launches_per_step': int(my_launches_per_step),
-            'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep,
+            'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep, 'scatter_kernels': scatter_kernels,
         }
     return line
+
+
+def scatter_microbench(dev, flush, peak, batch=131072):
+    """the layer-API scatter kernels (what the drop-in layers launch) at a batch where HBM traffic >> launch latency:
+    median of 5 event-timed launches, L2 flushed before each"""
+    from gsn_b200 import ops
+    b = build_batches(batch, 1, seed0=5)[0]
+    ei = torch.from_numpy(b['edge_index']).to(dev)
+    N, E, dh = int(b['node_ptr'][-1]), int(ei.shape[1]), D_OUT
+    plan = ops.EdgePlan(ei, N)
+    g = torch.Generator(device=dev).manual_seed(0)
+    P = torch.randn((N, 2 * dh), device=dev, generator=g)
+    Q = torch.randn((E, dh), device=dev, generator=g)
+    x = torch.randn((N, dh), device=dev, generator=g)
+    sc, sf = torch.rand(dh, device=dev) + 0.5, torch.randn(dh, device=dev)
+    csr = 8 * E + 4 * (N + 1)
+
+    def med(fn):
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return sorted(ts[2:])[2]
+    out = []
+    for name, fn, by in (
+            ('general_edge_kernel (GSN_edge_sparse general, dense P + Q)', lambda: ops.general_edge(plan, P, Q, sc, sf),
+             4 * 2 * dh * N + 4 * dh * E + 4 * dh * N + csr),
+            ('ogb_kernel (GSN_edge_sparse_ogb, local ids)', lambda: ops.ogb_aggregate(plan, x, Q, True, Q, None),
+             4 * dh * (2 * N + 2 * E) + csr),
+            ('segsum_kernel (scatter-add of [E,128] messages)', lambda: ops.segment_sum(plan, Q), 4 * dh * (N + E) + 4 * E + 4 * (N + 1))):
+        t = med(fn)
+        out.append({'kernel': name, 'batch': batch, 'N': N, 'E': E, 'us': t * 1e6, 'algorithmic_bytes': by,
+                    'GBps': by / t / 1e9, 'frac_of_peak': by / t / 1e9 / peak})
+    return out
 
 
 def sds_oracle():
