@@ -461,6 +461,42 @@ __global__ void __launch_bounds__(kMpThreads) general_edge_idx_kernel(const __gr
     o.st(p.S + row * dh + c);
 }
 
+// Lean specialisation for the layers without identifiers (layers >= 1 by default): dense P plus ONE categorical
+// edge column (e.g. the bond type), rows in CSR order.  Capped at 32 registers so that 2048 threads are resident
+// per SM: the kernel is bound by the latency of the L2-resident P_j gathers, and occupancy is what hides it.
+template <int VEC>
+__global__ void __launch_bounds__(kMpThreads, 8) general_edge_p1_kernel(const __grid_constant__ GenIdxParams p) {
+    const int dh = p.dh;
+    const int cpr = dh / VEC;
+    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t row = t / cpr;
+    const int c = (int)(t % cpr) * VEC;
+    const Vec<VEC> pi = Vec<VEC>::ld(p.P + row * (2 * dh) + c);
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    const float *Pj = p.P + dh + c;
+    const float *Te = p.Te + c;
+    const int kend = p.rowptr[row + 1];
+    for (int k = p.rowptr[row]; k < kend; ++k) {
+        const int j = __ldg(p.nbr + k);
+        const int r = __ldg(p.edge_rows + k);
+        const Vec<VEC> pj = Vec<VEC>::ld(Pj + (int64_t)j * (2 * dh));
+        const Vec<VEC> te = Vec<VEC>::ld(Te + (int64_t)r * dh);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float sc = p.scale ? __ldg(p.scale + c + i) : 1.0f;      // L1-resident; re-read to save registers
+            const float sf = p.shift ? __ldg(p.shift + c + i) : 0.0f;
+            acc[i] += apply_act(fmaf(pi.v[i] + pj.v[i] + te.v[i], sc, sf), p.act);
+        }
+    }
+    Vec<VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+    o.st(p.S + row * dh + c);
+}
+
 struct EncodeParams {
     GsnEncodeCol col[GSN_MAX_ENCODE_COLS];
     int n_cols;
@@ -660,6 +696,12 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool v4 = dh % 4 == 0 && aligned16(d_P) && aligned16(d_Q) && aligned16(d_S) && aligned16(d_Tn) && aligned16(d_Te);
     (void)te_rows;
+    if (v4 && d_P && !d_Q && n_node_cols == 0 && n_edge_cols == 1 && edge_rows_csr) {
+        general_edge_p1_kernel<4><<<(unsigned)ceil_div(N * (dh / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
+        GSN_BUMP(1);
+        GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");
+        return GSN_OK;
+    }
     if (v4) general_edge_idx_kernel<4><<<(unsigned)ceil_div(N * (dh / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
     else general_edge_idx_kernel<1><<<(unsigned)ceil_div(N * (int64_t)dh, kMpThreads), kMpThreads, 0, stream>>>(p);
     GSN_BUMP(1);

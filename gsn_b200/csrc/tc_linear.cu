@@ -177,9 +177,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             mbar_wait(&full_bar[s], ph);
             float4 *hi = reinterpret_cast<float4 *>(ring + (size_t)s * STAGE);
             float4 *lo = reinterpret_cast<float4 *>(ring + (size_t)s * STAGE + A_TILE);
+            // all loads first (the tile is converted in place, so the compiler cannot hoist them itself), then the
+            // conversions, then the stores: one shared-memory round trip per stage instead of eight
+            constexpr int NV = A_TILE / 16 / 128;
+            float4 av[NV];
 #pragma unroll
-            for (int i = 0; i < A_TILE / 16 / 128; ++i) {
-                float4 a = hi[tid + i * 128], h, l;
+            for (int i = 0; i < NV; ++i) av[i] = hi[tid + i * 128];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float4 a = av[i];
+                float4 h, l;
                 uint32_t u;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.x)); h.x = __uint_as_float(u);
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.y)); h.y = __uint_as_float(u);
