@@ -10,9 +10,10 @@
 // split_a_kernel into one [M, K1+K2] hi/lo pair (this also performs the
 // torch.cat((x, agg)) of graph_filters/GSN_edge_sparse.py:111).
 //
-// Warp roles (256 threads, one 128 x BN output tile per CTA):
+// Warp roles (384 threads, one 128 x BN output tile per CTA):
 //   warp 0 lane 0 : TMA producer          warp 1 lane 0 : MMA issuer
-//   warp 2        : TMEM alloc / dealloc  warps 4..7    : epilogue (tcgen05.ld -> registers -> global)
+//   warp 2        : TMEM alloc / dealloc  warps 4..11   : tf32 split of the landed A tile (in shared memory)
+//   warps 0..7    : epilogue (tcgen05.ld -> registers -> global)
 #include <cuda.h>
 #include "common.cuh"
 
@@ -73,7 +74,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 //                          warps 4-7 split every landed tile in shared memory (hi in place, lo next to it) while the
 //                          previous stage is being multiplied: no extra kernel, no extra HBM traffic.
 template <int BN, int STAGES, bool SPLIT_IN_KERNEL>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                  const __grid_constant__ TcEpilogue ep, int K1) {
@@ -102,7 +103,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
-            mbar_init(&conv_bar[s], 4);          // one arrival per converter warp
+            mbar_init(&conv_bar[s], 8);          // one arrival per converter warp (warps 4..11)
         }
         mbar_init(&tmem_full_bar, 1);
         mbar_fence_init();
@@ -170,7 +171,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (dbg) dbg[3] = clock64();
     } else if (SPLIT_IN_KERNEL && warp >= 4) {
         // ---------------- converters: raw fp32 tile -> (hi, lo) tf32 pair, elementwise in the swizzled layout
-        const int tid = threadIdx.x - 128;
+        const int tid = threadIdx.x - 128;        // 0..255: eight converter warps keep the split off the critical path
         for (int kt = 0; kt < nk; ++kt) {
             const int s = kt % STAGES;
             const uint32_t ph = (kt / STAGES) & 1;
@@ -179,10 +180,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             float4 *lo = reinterpret_cast<float4 *>(ring + (size_t)s * STAGE + A_TILE);
             // all loads first (the tile is converted in place, so the compiler cannot hoist them itself), then the
             // conversions, then the stores: one shared-memory round trip per stage instead of eight
-            constexpr int NV = A_TILE / 16 / 128;
+            constexpr int NV = A_TILE / 16 / 256;
             float4 av[NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) av[i] = hi[tid + i * 128];
+            for (int i = 0; i < NV; ++i) av[i] = hi[tid + i * 256];
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const float4 a = av[i];
@@ -196,8 +197,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.y - h.y)); l.y = __uint_as_float(u);
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.z - h.z)); l.z = __uint_as_float(u);
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.w - h.w)); l.w = __uint_as_float(u);
-                hi[tid + i * 128] = h;
-                lo[tid + i * 128] = l;
+                hi[tid + i * 256] = h;
+                lo[tid + i * 256] = l;
             }
             // generic-proxy writes must be visible to the tensor core (async proxy) before the MMA is issued
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -208,8 +209,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
     }
     __syncwarp();
-    {
-        // ---------------- epilogue (all 8 warps): TMEM lane = output row, one row per thread.
+    if (warp < 8) {
+        // ---------------- epilogue (warps 0..7): TMEM lane = output row, one row per thread.
         // Warp w may only touch TMEM lanes [32*(w%4), +32); warps 0-3 take the first half of the columns, warps
         // 4-7 the second half.  Each thread adds the two accumulators, applies the epilogue and writes its row
         // with 128-bit stores straight from registers (the L2 merges the sectors of a row).
@@ -388,7 +389,7 @@ static int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUt
         attr = true;
     }
     dim3 grid((unsigned)ceil_div(ep.M, TC_BM), (unsigned)ceil_div(ep.Nout, BN));
-    tc_linear_kernel<BN, STAGES, SPLIT><<<grid, 256, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, ep, K1);
+    tc_linear_kernel<BN, STAGES, SPLIT><<<grid, 384, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, ep, K1);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("tc_linear_kernel");
     return GSN_OK;
