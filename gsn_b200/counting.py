@@ -95,6 +95,8 @@ class BatchedGraph:
             out = torch.empty((rows, n_cols), dtype=torch.int64, device=dev)
         L = _lib.lib()
         scratch, scratch_bytes = None, 0
+        if rows == 0:
+            return out
         with torch.cuda.device(dev):
             for P in plans:
                 nb = ctypes.c_size_t(0)

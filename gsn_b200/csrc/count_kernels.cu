@@ -243,8 +243,10 @@ extern "C" int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t
                                  const int64_t *d_node_ptr, int64_t G, const GsnPlan *h_plan, int64_t *d_out,
                                  int64_t out_ld, void *d_scratch, size_t scratch_bytes, int32_t *d_status,
                                  void *stream_) {
-    if (!d_ws || !h_plan || !d_out || !d_status || !d_node_ptr || N < 0 || E < 0 || W < 1) return GSN_E_INVALID;
+    if (!d_ws || !h_plan || !d_status || !d_node_ptr || N < 0 || E < 0 || W < 1) return GSN_E_INVALID;
     const GsnPlan &P = *h_plan;
+    if (N == 0 || (P.scope == 1 && E == 0)) return GSN_OK;       // no output rows
+    if (!d_out) return GSN_E_INVALID;
     if (P.k < 2 || P.k > GSN_MAXK || P.n_cols < 1 || P.col0 < 0 || P.col0 + P.n_cols > out_ld) return GSN_E_INVALID;
     if (P.family != GSN_FAMILY_GENERIC && (P.kmin < 3 || P.kmax > GSN_MAXK || P.kmax < P.kmin)) return GSN_E_INVALID;
     if (W != 1 && W != 2 && W != 4 && W != 8 && W != 16) return GSN_E_UNSUPPORTED;

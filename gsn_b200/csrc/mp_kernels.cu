@@ -593,8 +593,10 @@ extern "C" int gsn_mp_gin_fwd(const int32_t *d_rowptr, const int32_t *d_eid, con
     bool v4 = aligned16(d_out);
     for (int i = 0; i < n_segs; ++i) {
         const GsnSegment &sg = h_segs[i];
-        if (sg.width < 1 || (sg.index_mode != 0 && !sg.src) || sg.index_mode < 0 || sg.index_mode > 2) return GSN_E_INVALID;
+        if (sg.width < 1 || sg.index_mode < 0 || sg.index_mode > 2) return GSN_E_INVALID;
+        if (sg.index_mode != 0 && !sg.src && E > 0) return GSN_E_INVALID;
         p.seg[i] = sg;
+        if (!sg.src) p.seg[i].index_mode = 0;        // E == 0: an empty per-edge matrix has no storage
         p.seg_off[i] = off;
         off += sg.width;
         v4 = v4 && sg.width % 4 == 0 && (sg.index_mode == 0 || (sg.src_ld % 4 == 0 && aligned16(sg.src))) &&
@@ -614,7 +616,7 @@ extern "C" int gsn_mp_gin_fwd(const int32_t *d_rowptr, const int32_t *d_eid, con
 extern "C" int gsn_mp_ogb_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
                               int64_t E, const float *d_x, const float *d_id, int32_t id_per_edge, const float *d_ef,
                               int32_t d, const float *d_eps, float *d_out, void *stream_) {
-    if (N < 0 || E < 0 || d < 1 || !d_rowptr || !d_x || !d_ef || !d_out) return GSN_E_INVALID;
+    if (N < 0 || E < 0 || d < 1 || !d_rowptr || !d_x || (!d_ef && E > 0) || !d_out) return GSN_E_INVALID;
     if (N == 0) return GSN_OK;
     OgbParams p{d_rowptr, d_eid, d_nbr, N, d_x, d_id, d_ef, d_eps, d, id_per_edge, d_out};
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -149,7 +149,10 @@ class SparseFilter(nn.Module):
     def _general(self, plan, x, identifiers, ef):
         f = self.msg_fn
         if f.depth != 2:
-            raise NotImplementedError('general message kind: msg_fn with num_mlp_layers != 2 is not built yet')
+            # deeper msg_fn (--num_mlp_layers > 2): the layers after the first activation act per edge, so the
+            # message is formed on E rows as in the reference and summed by the segment-sum kernel
+            from .autograd import forward_with_grad
+            return forward_with_grad(self, x, plan.edge_index, identifiers, ef)
         x = x.float()
         d_in = x.shape[1]
         d_id = identifiers.shape[1] if self.uses_ids else 0
