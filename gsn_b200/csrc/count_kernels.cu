@@ -295,7 +295,7 @@ extern "C" int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t
     if (acc_words * 4 > left) acc_words = left / 4;
     prm.T = (int32_t)T;
     // few items (small batch): split every directed edge into sub-items so that more threads share the search
-    prm.parts = E < (int64_t)kNumSMs * 512 ? 4 : (E < (int64_t)kNumSMs * 2048 ? 2 : 1);
+    prm.parts = E < (int64_t)kNumSMs * 128 ? 8 : (E < (int64_t)kNumSMs * 512 ? 4 : (E < (int64_t)kNumSMs * 2048 ? 2 : 1));
     prm.smem_adj_words = (int32_t)adj_words;
     prm.smem_row_words = (int32_t)row_words;
     prm.smem_acc_words = (int32_t)acc_words;

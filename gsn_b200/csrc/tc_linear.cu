@@ -219,6 +219,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (dbg && threadIdx.x == 128) dbg[4] = clock64();
         const int wq = warp & 3;
         const int half = warp >> 2;
+        constexpr int HALF_COLS = BN >= 64 ? BN / 2 : BN;      // BN = 32: one 32-column chunk, warps 0..3 only
         const int m = m0 + wq * 32 + lane;
         const bool mok = m < ep.M;
         const bool accumulate = ep.accumulate == 1;
@@ -230,7 +231,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         float *crow = ep.C + (int64_t)(mok ? m : 0) * ep.ldc;
         const bool vec = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
 #pragma unroll 1
-        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        for (int c0 = half * HALF_COLS; c0 < (half + 1) * HALF_COLS && c0 < BN; c0 += 32) {
             uint32_t r[32], q[32];
             const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
             asm volatile(
@@ -429,7 +430,11 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
     if ((p.row_scale == nullptr) != (p.row_vec == nullptr) || (p.tab == nullptr) != (p.tab_idx == nullptr)) return GSN_E_INVALID;
     if (p.M == 0) return GSN_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int BN = p.Nout > 128 ? 256 : (p.Nout > 64 ? 128 : 64);
+    // wide tiles for throughput; when the grid would leave most SMs idle, narrow tiles give more CTAs and a deeper
+    // ring (5 stages of 40 KB at BN = 32) so that a small GEMM is not bound by the TMA round-trip per stage
+    int BN = p.Nout > 128 ? 256 : (p.Nout > 64 ? 128 : 64);
+    const int64_t m_tiles = ceil_div(p.M, TC_BM);
+    if (m_tiles * ceil_div(p.Nout, BN) < kNumSMs / 2 && p.Nout >= 32) BN = 32;
     TcEpilogue ep{p.bias, p.row_scale, p.row_vec, p.tab, p.scale, p.shift, p.tab_idx, p.C,
                   p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate, (long long *)g_tc_debug};
     CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
@@ -442,6 +447,7 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
         if ((rc = make_map(&mA_hi, p.A1, p.M, p.K1, p.lda1, TC_BM))) return rc;
         if (p.K2 > 0) { if ((rc = make_map(&mA_lo, p.A2, p.M, p.K2, p.lda2, TC_BM))) return rc; }
         else mA_lo = mA_hi;
+        if (BN == 32) return launch_tc<32, 5, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
         if (BN == 256) return launch_tc<256, 2, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
         if (BN == 128) return launch_tc<128, 3, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
         return launch_tc<64, 4, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
@@ -456,6 +462,7 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
     GSN_BUMP(1);
     if ((rc = make_map(&mA_hi, a_hi, p.M, K, K, TC_BM))) return rc;
     if ((rc = make_map(&mA_lo, a_lo, p.M, K, K, TC_BM))) return rc;
+    if (BN == 32) return launch_tc<32, 5, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
     if (BN == 256) return launch_tc<256, 2, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
     if (BN == 128) return launch_tc<128, 3, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
     return launch_tc<64, 4, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);

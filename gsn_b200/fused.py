@@ -176,11 +176,14 @@ class FusedForward:
             id_off.append(o)
             o += int(d)
         if vocab is not None:
-            vcat = torch.cat(vocab)
-            vptr, o2 = [], 0
-            for v in vocab:
-                vptr.append((o2, o2 + v.numel()))
-                o2 += v.numel()
+            key = tuple((v.data_ptr(), v.numel()) for v in vocab)
+            if getattr(self, '_vocab_key', None) != key:           # concatenated once, not once per step
+                self._vocab_key, self._vcat = key, torch.cat(vocab)
+                self._vptr, o2 = [], 0
+                for v in vocab:
+                    self._vptr.append((o2, o2 + v.numel()))
+                    o2 += v.numel()
+            vcat, vptr = self._vcat, self._vptr
         else:
             vcat, vptr = None, [None] * len(id_dims)
 

@@ -70,7 +70,7 @@ class EdgePlan:
     def degree(self) -> torch.Tensor:
         """number of aggregated messages per node, float32 [N]"""
         if self._deg is None:
-            self._deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)
+            self._deg = torch.diff(self.rowptr).to(torch.float32)
         return self._deg
 
     def raise_on_status(self):

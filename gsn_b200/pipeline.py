@@ -64,6 +64,7 @@ class GSNPipeline:
         self._static: Dict[str, torch.Tensor] = {}
         self._out: Optional[torch.Tensor] = None
         self.last_status: Optional[torch.Tensor] = None
+        self._side: Optional[torch.cuda.Stream] = None
 
     # -- one eager step on device-resident inputs --------------------------------
     def step(self, t: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -71,10 +72,20 @@ class GSNPipeline:
         ops.clear_plan_cache()            # a step is a new batch: never reuse groupings across steps
         encoders._pool_plans.clear()
         N, G = int(t['x'].shape[0]), int(t['node_ptr'].numel() - 1)
+        # the grouping of edge_index for the message kernels does not depend on COUNT: build it on a side stream
+        # while the counting kernels run (a fork / join that CUDA-graph capture records as parallel branches)
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            flow = self.model.conv[0].flow
+            ops.edge_plan(t['edge_index'], N, flow).degree()
         graph = counting.BatchedGraph(t['edge_index'], t['node_ptr'], num_nodes=N, max_nodes_per_graph=self.max_nodes)
         ids = counting.count_batch(t['edge_index'], t['node_ptr'], self.subgraph_dicts, self.induced, self.id_scope,
                                    num_nodes=N, max_nodes_per_graph=self.max_nodes, check=False, graph=graph)
         self.last_status = graph.status
+        cur.wait_stream(self._side)
         if self.fused is not None:
             data = Batch(x=t['x'], edge_index=t['edge_index'], edge_features=t['edge_features'], batch=t['batch'],
                          degrees=t['degrees'], node_ptr=t['node_ptr'], num_graphs=G)
