@@ -317,6 +317,248 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant for large problems: one CTA per SM loops over output tiles; the TMA -> split -> MMA ring
+// runs continuously across tiles and the accumulator is double-buffered in TMEM, so the epilogue of tile i
+// overlaps the main loop of tile i+1 (the one-tile kernel above exposes prologue + pipeline fill + epilogue on
+// every tile: ~18 k cycles per tile of which ~8 k are MMA work).
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-11: tf32 split   warps 12-15: epilogue
+// Activations are always split in the kernel (raw A1 [M,K1] / A2 [M,K2], K1 % 32 == 0 when K2 > 0).
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(512, 1)
+tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                            const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                            const __grid_constant__ TcEpilogue ep, int K1, int m_tiles, int n_tiles) {
+    constexpr int A_TILE = TC_BM * TC_BK * 4;
+    constexpr int W_TILE = BN * TC_BK * 4;
+    constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], conv_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = (ep.K + TC_BK - 1) / TC_BK;
+    const int total_tiles = m_tiles * n_tiles;
+    unsigned char *ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_lo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&conv_bar[s], 8);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full_bar[b], 1);
+            mbar_init(&tmem_empty_bar[b], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"((uint32_t)(4 * BN))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+            for (int kt = 0; kt < nk; ++kt, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                unsigned char *st = ring + (size_t)s * STAGE;
+                const int k0 = kt * TC_BK;
+                mbar_arrive_expect_tx(&full_bar[s], A_TILE + 2 * W_TILE);
+                if (k0 < K1) tma_load_2d(st, &tmA1, k0, m0, &full_bar[s]);
+                else tma_load_2d(st, &tmA2, k0 - K1, m0, &full_bar[s]);
+                tma_load_2d(st + 2 * A_TILE, &tmW_hi, k0, n0, &full_bar[s]);
+                tma_load_2d(st + 2 * A_TILE + W_TILE, &tmW_lo, k0, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        int it = 0, tc = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+            const int b = tc & 1;
+            mbar_wait(&tmem_empty_bar[b], ((tc >> 1) & 1) ^ 1);          // the epilogue has drained this buffer
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc_main = tmem_d + (uint32_t)(b * 2 * BN), acc_corr = acc_main + BN;
+            for (int kt = 0; kt < nk; ++kt, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&conv_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned char *st = ring + (size_t)s * STAGE;
+                const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + A_TILE);
+                const uint64_t w_hi = umma_desc(st + 2 * A_TILE), w_lo = umma_desc(st + 2 * A_TILE + W_TILE);
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
+                    const uint32_t first = (kt > 0 || k > 0) ? 1u : 0u;
+                    umma_tf32(acc_main, a_hi + adv, w_hi + adv, idesc, first);
+                    umma_tf32(acc_corr, a_lo + adv, w_hi + adv, idesc, first);
+                    umma_tf32(acc_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar[b]);
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ---------------- converters
+        const int tid = threadIdx.x - 128;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int kt = 0; kt < nk; ++kt, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                float4 *hi = reinterpret_cast<float4 *>(ring + (size_t)s * STAGE);
+                float4 *lo = reinterpret_cast<float4 *>(ring + (size_t)s * STAGE + A_TILE);
+                constexpr int NV = A_TILE / 16 / 256;
+                float4 av[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) av[i] = hi[tid + i * 256];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const float4 a = av[i];
+                    float4 h, l;
+                    uint32_t u;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.x)); h.x = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.y)); h.y = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.z)); h.z = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.w)); h.w = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.x - h.x)); l.x = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.y - h.y)); l.y = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.z - h.z)); l.z = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a.w - h.w)); l.w = __uint_as_float(u);
+                    hi[tid + i * 256] = h;
+                    lo[tid + i * 256] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
+            }
+        }
+    } else if (warp >= 12) {
+        // ---------------- epilogue: one output row per thread, all BN columns
+        const int wq = warp & 3;
+        const bool accumulate = ep.accumulate == 1;
+        const int act = ep.act;
+        const float *bias = ep.bias, *row_vec = ep.row_vec, *scale = ep.scale, *shift = ep.shift;
+        const bool vec = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
+        int tc = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+            const int b = tc & 1;
+            const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+            mbar_wait(&tmem_full_bar[b], (tc >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = m0 + wq * 32 + lane;
+            const bool mok = m < ep.M;
+            const float rs = (ep.row_scale && mok) ? __ldg(ep.row_scale + m) : 0.f;
+            const float *trow = (ep.tab && mok) ? ep.tab + (int64_t)__ldg(ep.tab_idx + m) * ep.tab_ld : nullptr;
+            float *crow = ep.C + (int64_t)(mok ? m : 0) * ep.ldc;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32], q[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * 2 * BN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+                      "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]),
+                      "=r"(q[16]), "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]),
+                      "=r"(q[24]), "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+                    : "r"(taddr + (uint32_t)BN)
+                    : "memory");
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int nb = n0 + c0;
+                if (mok && nb < ep.Nout) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(q[j]);
+                    const bool whole = nb + 32 <= ep.Nout;
+                    if (row_vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, (whole || nb + j < ep.Nout) ? __ldg(row_vec + nb + j) : 0.f, v[j]);
+                    }
+                    if (trow) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += (whole || nb + j < ep.Nout) ? __ldg(trow + nb + j) : 0.f;
+                    }
+                    if (bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += (whole || nb + j < ep.Nout) ? __ldg(bias + nb + j) : 0.f;
+                    }
+                    if (scale) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= (whole || nb + j < ep.Nout) ? __ldg(scale + nb + j) : 1.f;
+                    }
+                    if (shift) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += (whole || nb + j < ep.Nout) ? __ldg(shift + nb + j) : 0.f;
+                    }
+                    if (act == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (act != 3) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = tc_act_slow(v[j], act);
+                    }
+                    if (accumulate) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (whole || nb + j < ep.Nout) v[j] += crow[nb + j];
+                    }
+                    if (vec && whole) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < ep.Nout) crow[nb + j] = v[j];
+                    }
+                }
+            }
+            // this warp is done reading accumulator buffer b: hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[b])) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(4 * BN)) : "memory");
+    }
+}
+
 // x -> (rn_tf32(x), x - rn_tf32(x)) ; two row-major sources concatenated along K into [M, K1+K2]
 __global__ void split_a_kernel(const float *__restrict__ A1, int K1, int lda1, const float *__restrict__ A2, int K2,
                                int lda2, int64_t M, float *__restrict__ hi, float *__restrict__ lo) {
@@ -345,6 +587,7 @@ __global__ void split_a_kernel(const float *__restrict__ A1, int K1, int lda1, c
 
 void *g_tc_debug = nullptr;
 bool g_tc_force_presplit = false;     // testing aid: exercise the split_a_kernel path
+bool g_tc_no_persistent = false;      // testing aid: keep large problems on the one-tile kernel
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -393,6 +636,24 @@ static int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUt
     tc_linear_kernel<BN, STAGES, SPLIT><<<grid, 384, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, ep, K1);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("tc_linear_kernel");
+    return GSN_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc_persistent(const CUtensorMap &a1, const CUtensorMap &a2, const CUtensorMap &w_hi, const CUtensorMap &w_lo,
+                                const TcEpilogue &ep, int K1, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    const int m_tiles = (int)ceil_div(ep.M, TC_BM), n_tiles = (int)ceil_div(ep.Nout, BN);
+    const int64_t total = (int64_t)m_tiles * n_tiles;
+    const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
+    tc_linear_persistent_kernel<BN, STAGES><<<grid, 512, smem, stream>>>(a1, a2, w_hi, w_lo, ep, K1, m_tiles, n_tiles);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("tc_linear_persistent_kernel");
     return GSN_OK;
 }
 
@@ -447,6 +708,16 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
         if ((rc = make_map(&mA_hi, p.A1, p.M, p.K1, p.lda1, TC_BM))) return rc;
         if (p.K2 > 0) { if ((rc = make_map(&mA_lo, p.A2, p.M, p.K2, p.lda2, TC_BM))) return rc; }
         else mA_lo = mA_hi;
+        // large problems: persistent kernel (continuous ring, double-buffered TMEM accumulators)
+        const int BNp = p.Nout > 64 ? 128 : 64;
+        if (!g_tc_no_persistent && m_tiles * ceil_div(p.Nout, BNp) >= 2 * kNumSMs) {
+            if (BNp != BN) {
+                if ((rc = make_map(&mW_hi, d_Whi, p.Nout, K, K, BNp))) return rc;
+                if ((rc = make_map(&mW_lo, d_Wlo, p.Nout, K, K, BNp))) return rc;
+            }
+            if (BNp == 128) return launch_tc_persistent<128, 3>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
+            return launch_tc_persistent<64, 4>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
+        }
         if (BN == 32) return launch_tc<32, 5, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
         if (BN == 256) return launch_tc<256, 2, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
         if (BN == 128) return launch_tc<128, 3, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
@@ -470,4 +741,8 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
 
 // profiling aid: when set, every tc_linear CTA writes 8 clock64 stamps to d_buf[cta*8 ..]
 extern "C" int gsn_tc_debug_buffer(void *d_buf) { gsn::g_tc_debug = d_buf; return GSN_OK; }
-extern "C" int gsn_tc_force_presplit(int on) { gsn::g_tc_force_presplit = on != 0; return GSN_OK; }
+extern "C" int gsn_tc_force_presplit(int on) {
+    gsn::g_tc_force_presplit = (on & 1) != 0;
+    gsn::g_tc_no_persistent = (on & 2) != 0;
+    return GSN_OK;
+}

@@ -254,7 +254,8 @@ int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const float *d_W
                       void *stream);
 /* Profiling aid: non-NULL -> every tc_linear CTA writes 8 clock64 stamps to d_buf[cta*8..]; NULL disables. */
 int gsn_tc_debug_buffer(void *d_buf);
-/* Testing aid: 1 forces the pre-split path (split_a_kernel + workspace) even when the in-kernel split applies. */
+/* Testing aid (bit mask): 1 forces the pre-split path (split_a_kernel + workspace) even when the in-kernel split
+ * applies; 2 keeps large problems on the one-tile kernel instead of the persistent one. */
 int gsn_tc_force_presplit(int on);
 
 /*

@@ -17,7 +17,8 @@ MODEL_GOLDEN = torch.load(os.path.join(GOLDEN, 'mp_models.pt'))
 @pytest.mark.parametrize('mode', ['auto', 'off', 'presplit'])
 @pytest.mark.parametrize('M,K1,K2,Nout', [(1, 7, 0, 5), (37, 28, 0, 256), (130, 128, 128, 128), (2924, 156, 0, 128),
                                           (5000, 64, 33, 70), (70000, 128, 128, 128), (128, 128, 0, 1), (300, 8, 0, 24),
-                                          (1000, 300, 0, 600), (513, 600, 0, 300), (260, 128, 4, 200)])
+                                          (1000, 300, 0, 600), (513, 600, 0, 300), (260, 128, 4, 200),
+                                          (40000, 128, 0, 256), (38000, 64, 0, 70), (60000, 32, 0, 48), (45000, 128, 128, 128)])
 def test_linear_kernel_vs_torch(M, K1, K2, Nout, mode, monkeypatch):
     """fp32 FFMA kernel (mode off) and tcgen05 3xTF32 kernel (mode auto, where shapes allow)"""
     from gsn_b200 import ops
