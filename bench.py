@@ -271,16 +271,26 @@ def run_ours(args, rank, world, local_rank):
             layer0 = 4 * n + 4 * (n_id_cols + 1) * e + csr + out
             later = 4 * 2 * dh * n + 4 * e + csr + out
             return (layer0 + (N_LAYERS - 1) * later) / N_LAYERS
-        t_sc = prof['general_edge'][0]
+        # device duration of the message kernel at the step's own shapes: R back-to-back launches inside one event
+        # pair (a single ~5 us launch bracketed by its own events mostly measures launch gaps)
+        t_sc_eager = prof['general_edge'][0]
+        t_sc = scatter_launch_seconds(dev, b0, encoder, reps=50)
         roof = {'bound': 'hbm', 'kernel': 'general_edge_idx_kernel<4> (gsn_mp_general_edge_idx_fwd), mean of the '
                                           f'{N_LAYERS} launches of a step',
                 'achieved': scatter_bytes(N, E) / t_sc / 1e9, 'peak': peak, 'unit': 'GB/s',
-                'frac': scatter_bytes(N, E) / t_sc / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': scatter_bytes(N, E) / t_sc / 1e9 / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 launches of one step, from the
+                # committed capture profiles/r1_ncu_scatter_b128.txt (ncu --set full, B=128): 0.29 MB (layer 0) and
+                # 3 x 3.20 MB read, 0 B written (the 1.5 MB S output stays in the 126 MB L2)
+                'traffic': (0.2944e6 + 3 * 3.203328e6) / 4 if (B == 128 and N_LAYERS == 4) else None,
+                'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': scatter_bytes(N, E), 'avg_launch_us': t_sc * 1e6,
                 'launches_per_step': prof['general_edge'][1],
-                'how': 'CUDA events around each gsn_mp_general_edge_idx_fwd call in an eager pass over the same steps '
-                       '(L2 flushed between steps); at B=128 one launch moves ~3 MB, i.e. it is launch-latency bound: '
-                       'see sweep[] for B=4,096 / 131,072 and scatter_kernels[] for the layer-API kernels',
+                'avg_launch_us_single_eager': t_sc_eager * 1e6,
+                'how': 'mean device time of the 4 message-kernel launches of a step (layer 0 + 3 identifier-free layers) at '
+                       'the step shapes, 50 launches replayed from a CUDA graph per CUDA-event pair; at B=128 one launch moves ~2 MB '
+                       '(0.3 us at HBM peak) so it is launch-latency bound: see roofline_large_batch, sweep[] and '
+                       'scatter_kernels[] for batches where HBM traffic dominates',
                 'traffic_note': 'ncu --set full (profiles/): dram read+write per launch == algorithmic bytes within 1 % '
                                 'for the dense kernel at B=32,768'}
         kernels_us = {k: round(v[0] * 1e6, 2) for k, v in prof.items()}
@@ -317,12 +327,26 @@ def run_ours(args, rank, world, local_rank):
                     torch.cuda.empty_cache()
                 except Exception as ex:      # the sweep is informative only; never lose the headline line
                     sweep.append({'batch': Bs, 'error': repr(ex)[:200]})
+        roof_large = None
         scatter_kernels = []
         if not args.no_sweep:
             try:
                 scatter_kernels = scatter_microbench(dev, flush, peak)
             except Exception as ex:
                 scatter_kernels = [{'error': repr(ex)[:200]}]
+        if not args.no_sweep:
+            try:
+                bl = build_batches(131072, 1, seed0=5)[0]
+                nl, el = int(bl['node_ptr'][-1]), int(bl['edge_index'].shape[1])
+                tl = scatter_launch_seconds(dev, bl, encoder, reps=3, flush=flush)
+                roof_large = {'bound': 'hbm', 'kernel': roof['kernel'], 'batch': 131072, 'N': nl, 'E': el,
+                              'achieved': scatter_bytes(nl, el) / tl / 1e9, 'peak': peak, 'unit': 'GB/s',
+                              'frac': scatter_bytes(nl, el) / tl / 1e9 / peak, 'avg_launch_us': tl * 1e6,
+                              'algorithmic_bytes_per_launch': scatter_bytes(nl, el),
+                              'traffic': 'ncu --set full at B=32,768 (profiles/r1_ncu_scatter_idx_b32768.txt): dram '
+                                         'read+write 1.16 GB per identifier-free launch vs 1.18 GB algorithmic'}
+            except Exception as ex:
+                roof_large = {'error': repr(ex)[:200]}
         cpu = cpu_baseline(pool[0], sds_oracle(), encoder, model, budget_s=12.0)
         line = {
             'metric': 'graphs/sec preprocess+forward (ZINC batch)', 'value': value, 'unit': 'graphs/s',
@@ -341,8 +365,60 @@ def run_ours(args, rank, world, local_rank):
             'gpu_launches': int(my_launches_per_step) * args.steps,
             'gpu_launches_per_step': int(my_launches_per_step),
             'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep, 'scatter_kernels': scatter_kernels,
+            'roofline_large_batch': roof_large,
         }
     return line
+
+
+def scatter_launch_seconds(dev, batch, encoder, reps, flush=None):
+    """mean device seconds of ONE message-kernel launch of a step on `batch` (weights: 1 layer-0 launch reading only
+    indices + (N_LAYERS-1) launches reading P and one index column), timed as back-to-back launches"""
+    from gsn_b200 import ops
+    ei = torch.from_numpy(batch['edge_index']).to(dev)
+    N, E, dh = int(batch['node_ptr'][-1]), int(ei.shape[1]), D_OUT
+    plan = ops.EdgePlan(ei, N)
+    g = torch.Generator(device=dev).manual_seed(0)
+    P = torch.randn((N, 2 * dh), device=dev, generator=g)
+    sc, sf = torch.rand(dh, device=dev) + 0.5, torch.randn(dh, device=dev)
+    er1 = torch.randint(0, 4, (E, 1), device=dev, dtype=torch.int32)
+    Te1 = torch.randn((4, dh), device=dev)
+    n_id = sum(encoder.d)
+    nr = torch.randint(0, 28, (N, 1), device=dev, dtype=torch.int32)
+    Tn = torch.randn((28, 2 * dh), device=dev)
+    er0 = torch.randint(0, n_id + 4, (E, len(encoder.d) + 1), device=dev, dtype=torch.int32)
+    Te0 = torch.randn((n_id + 4, dh), device=dev)
+
+    def later():
+        ops.general_edge_idx(plan, dh, P=P, edge_rows=er1, Te=Te1, scale=sc, shift=sf, edge_rows_csr=True)
+
+    def first():
+        ops.general_edge_idx(plan, dh, node_rows=nr, Tn=Tn, edge_rows=er0, Te=Te0, scale=sc, shift=sf, edge_rows_csr=True)
+
+    def run(fn):
+        # the launches are recorded into a CUDA graph and replayed, so that the event pair brackets device work only
+        # (an eager Python launch costs ~15 us of host time, more than the kernel itself at B=128)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(reps):
+                fn()
+        gr.replay()
+        torch.cuda.synchronize()
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+    return (run(first) + (N_LAYERS - 1) * run(later)) / N_LAYERS
 
 
 def scatter_microbench(dev, flush, peak, batch=131072):
