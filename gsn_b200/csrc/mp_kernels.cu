@@ -497,6 +497,50 @@ __global__ void __launch_bounds__(kMpThreads, 8) general_edge_p1_kernel(const __
     o.st(p.S + row * dh + c);
 }
 
+// Lean specialisation for the fully categorical layer (layer 0 of the ZINC / IMDB recipes): no dense operand at
+// all, one node column (atom type) and C edge columns (identifier ranks, bond type), edge rows in CSR order.
+// 32 registers (full occupancy): every term is an L1/L2-resident table row reached through a dependent index load.
+template <int VEC>
+__global__ void __launch_bounds__(kMpThreads, 8) general_edge_tab_kernel(const __grid_constant__ GenIdxParams p) {
+    const int dh = p.dh;
+    const int cpr = dh / VEC;
+    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t row = t / cpr;
+    const int c = (int)(t % cpr) * VEC;
+    const int C = p.n_edge_cols;
+    const Vec<VEC> ti = Vec<VEC>::ld(p.Tn + (int64_t)__ldg(p.node_rows + row) * (2 * dh) + c);
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    const float *Tj = p.Tn + dh + c;
+    const float *Te = p.Te + c;
+    const int kend = p.rowptr[row + 1];
+    for (int k = p.rowptr[row]; k < kend; ++k) {
+        const int j = __ldg(p.nbr + k);
+        const Vec<VEC> tj = Vec<VEC>::ld(Tj + (int64_t)__ldg(p.node_rows + j) * (2 * dh));
+        float h[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) h[i] = ti.v[i] + tj.v[i];
+        const int32_t *er = p.edge_rows + (int64_t)k * C;
+        for (int q = 0; q < C; ++q) {
+            const Vec<VEC> te = Vec<VEC>::ld(Te + (int64_t)__ldg(er + q) * dh);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) h[i] += te.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float sc = p.scale ? __ldg(p.scale + c + i) : 1.0f;
+            const float sf = p.shift ? __ldg(p.shift + c + i) : 0.0f;
+            acc[i] += apply_act(fmaf(h[i], sc, sf), p.act);
+        }
+    }
+    Vec<VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+    o.st(p.S + row * dh + c);
+}
+
 struct EncodeParams {
     GsnEncodeCol col[GSN_MAX_ENCODE_COLS];
     int n_cols;
@@ -698,6 +742,12 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool v4 = dh % 4 == 0 && aligned16(d_P) && aligned16(d_Q) && aligned16(d_S) && aligned16(d_Tn) && aligned16(d_Te);
     (void)te_rows;
+    if (v4 && !d_P && !d_Q && n_node_cols == 1 && n_edge_cols >= 1 && edge_rows_csr) {
+        general_edge_tab_kernel<4><<<(unsigned)ceil_div(N * (dh / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
+        GSN_BUMP(1);
+        GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");
+        return GSN_OK;
+    }
     if (v4 && d_P && !d_Q && n_node_cols == 0 && n_edge_cols == 1 && edge_rows_csr) {
         general_edge_p1_kernel<4><<<(unsigned)ceil_div(N * (dh / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
         GSN_BUMP(1);
