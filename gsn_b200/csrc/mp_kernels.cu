@@ -497,6 +497,190 @@ __global__ void __launch_bounds__(kMpThreads, 8) general_edge_p1_kernel(const __
     o.st(p.S + row * dh + c);
 }
 
+// Tight specialisations of the two lean kernels.  ncu on the lean form (B = 131,072): 303 warp instructions per row,
+// issue slots 63 % busy, l1tex data pipe 88 % -- the kernel was bound by its own instruction stream (64-bit div/mod
+// for the (row, chunk) split, per-element null checks, scale / shift re-reads), not by DRAM.  Here: dh/4 is a power
+// of two (shift / mask), all offsets are 32-bit element indices, the activation is a template parameter and the
+// BatchNorm affine is folded into the operands upstream (gsn_b200/fused.py), so an edge costs ~25 instructions.
+template <int ACT> __device__ __forceinline__ float act_t(float v, int act) {
+    return ACT == 0 ? fmaxf(v, 0.0f) : (ACT == 3 ? v : apply_act_slow(v, act));
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kMpThreads, 8)
+p1_tight_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ nbr, const int32_t *__restrict__ er,
+                const float4 *__restrict__ P4, const float4 *__restrict__ Te4, float4 *__restrict__ S4,
+                uint32_t total, int sh, int act) {
+    const uint32_t t = blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= total) return;
+    const uint32_t row = t >> sh, c4 = t & ((1u << sh) - 1u);
+    int k = __ldg(rowptr + row);
+    const int kend = __ldg(rowptr + row + 1);
+    const float4 pi = __ldg(P4 + ((row << (sh + 1)) + c4));
+    const float4 *Pj = P4 + ((1u << sh) + c4);
+    const float4 *Te = Te4 + c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; k < kend; ++k) {
+        const uint32_t j = (uint32_t)__ldg(nbr + k), r = (uint32_t)__ldg(er + k);
+        const float4 pj = __ldg(Pj + (j << (sh + 1)));
+        const float4 te = __ldg(Te + (r << sh));
+        acc.x += act_t<ACT>(pi.x + pj.x + te.x, act);
+        acc.y += act_t<ACT>(pi.y + pj.y + te.y, act);
+        acc.z += act_t<ACT>(pi.z + pj.z + te.z, act);
+        acc.w += act_t<ACT>(pi.w + pj.w + te.w, act);
+    }
+    S4[t] = acc;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kMpThreads, 8)
+tab_tight_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ nbr, const int32_t *__restrict__ nr,
+                 const int32_t *__restrict__ er, int C, const float4 *__restrict__ Tn4, const float4 *__restrict__ Te4,
+                 float4 *__restrict__ S4, uint32_t total, int sh, int act) {
+    const uint32_t t = blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= total) return;
+    const uint32_t row = t >> sh, c4 = t & ((1u << sh) - 1u);
+    int k = __ldg(rowptr + row);
+    const int kend = __ldg(rowptr + row + 1);
+    const float4 ti = __ldg(Tn4 + (((uint32_t)__ldg(nr + row) << (sh + 1)) + c4));
+    const float4 *Tj = Tn4 + ((1u << sh) + c4);
+    const float4 *Te = Te4 + c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; k < kend; ++k) {
+        const uint32_t j = (uint32_t)__ldg(nbr + k);
+        const float4 tj = __ldg(Tj + ((uint32_t)__ldg(nr + j) << (sh + 1)));
+        float4 h = make_float4(ti.x + tj.x, ti.y + tj.y, ti.z + tj.z, ti.w + tj.w);
+        const int32_t *e = er + (uint32_t)k * (uint32_t)C;
+        for (int q = 0; q < C; ++q) {
+            const float4 te = __ldg(Te + ((uint32_t)__ldg(e + q) << sh));
+            h.x += te.x; h.y += te.y; h.z += te.z; h.w += te.w;
+        }
+        acc.x += act_t<ACT>(h.x, act);
+        acc.y += act_t<ACT>(h.y, act);
+        acc.z += act_t<ACT>(h.z, act);
+        acc.w += act_t<ACT>(h.w, act);
+    }
+    S4[t] = acc;
+}
+
+// Variant of the lean kernel that keeps the L1 data pipe free for the row gathers (ncu: the lean kernel sits at 88 %
+// of l1tex data-pipe wavefronts, not at DRAM): the BatchNorm affine is either folded upstream (AFFINE = false) or kept
+// in registers, and a table of <= 4 categorical rows (the bond types) lives in registers instead of being re-read.
+template <bool TE_REGS, bool AFFINE>
+__global__ void __launch_bounds__(kMpThreads, 6) general_edge_p1b_kernel(const __grid_constant__ GenIdxParams p, int te_rows) {
+    const int dh = p.dh;
+    const int cpr = dh / 4;
+    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t row = t / cpr;
+    const int c = (int)(t % cpr) * 4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pi = __ldg(reinterpret_cast<const float4 *>(p.P + row * (2 * dh) + c));
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = z;
+    if (AFFINE) {
+        if (p.scale) sc = __ldg(reinterpret_cast<const float4 *>(p.scale + c));
+        if (p.shift) sf = __ldg(reinterpret_cast<const float4 *>(p.shift + c));
+        // (pi + pj + te) * sc + sf  ==  fma(pj + te, sc, fma(pi, sc, sf)) up to rounding; keep the reference order instead
+    }
+    float4 t0 = z, t1 = z, t2 = z, t3 = z;
+    if (TE_REGS) {
+        const float4 *T = reinterpret_cast<const float4 *>(p.Te + c);
+        t0 = __ldg(T);
+        if (te_rows > 1) t1 = __ldg(T + (dh / 4));
+        if (te_rows > 2) t2 = __ldg(T + 2 * (dh / 4));
+        if (te_rows > 3) t3 = __ldg(T + 3 * (dh / 4));
+    }
+    float4 acc = z;
+    const float *Pj = p.P + dh + c;
+    const float *Te = p.Te + c;
+    const int kend = p.rowptr[row + 1];
+    for (int k = p.rowptr[row]; k < kend; ++k) {
+        const int j = __ldg(p.nbr + k);
+        const int r = __ldg(p.edge_rows + k);
+        const float4 pj = __ldg(reinterpret_cast<const float4 *>(Pj + (int64_t)j * (2 * dh)));
+        float4 te;
+        if (TE_REGS) te = r == 0 ? t0 : (r == 1 ? t1 : (r == 2 ? t2 : t3));
+        else te = __ldg(reinterpret_cast<const float4 *>(Te + (int64_t)r * dh));
+        float4 h = make_float4(pi.x + pj.x + te.x, pi.y + pj.y + te.y, pi.z + pj.z + te.z, pi.w + pj.w + te.w);
+        if (AFFINE) { h.x = fmaf(h.x, sc.x, sf.x); h.y = fmaf(h.y, sc.y, sf.y); h.z = fmaf(h.z, sc.z, sf.z); h.w = fmaf(h.w, sc.w, sf.w); }
+        acc.x += apply_act(h.x, p.act); acc.y += apply_act(h.y, p.act);
+        acc.z += apply_act(h.z, p.act); acc.w += apply_act(h.w, p.act);
+    }
+    *reinterpret_cast<float4 *>(p.S + row * dh + c) = acc;
+}
+
+// Warp-cooperative form of the same layer: one warp owns G consecutive rows (all dh channels, 4 per lane per
+// 128-column pass).  The index chain rowptr -> nbr -> P_j that every thread of the lean kernel walks on its own is
+// walked ONCE per warp: lanes 0..G fetch the row pointers, the warp fetches up to 32 neighbour ids / bond rows with
+// one coalesced load each, and the values are handed round with shfl.  The gathers of U edges plus the G own rows
+// are all issued before the first is consumed, so each lane keeps (U + G) x 16 B in flight instead of 16 B.
+template <int G, int U>
+__global__ void __launch_bounds__(kMpThreads) general_edge_p1_warp_kernel(const __grid_constant__ GenIdxParams p) {
+    const int dh = p.dh;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kMpThreads + threadIdx.x) >> 5;
+    const int64_t r0 = warp * G;
+    if (r0 >= p.N) return;
+    const int nrows = (int)min((int64_t)G, p.N - r0);
+    const int rp = __ldg(p.rowptr + r0 + min(lane, nrows));
+    const int kb = __shfl_sync(0xffffffffu, rp, 0), ke = __shfl_sync(0xffffffffu, rp, nrows);
+    for (int cb = 0; cb < dh; cb += 128) {
+        const int c = cb + lane * 4;
+        const bool on = c < dh;
+        float4 pi[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            pi[g] = (on && g < nrows) ? __ldg(reinterpret_cast<const float4 *>(p.P + (r0 + g) * (2 * dh) + c))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on && p.scale) sc = __ldg(reinterpret_cast<const float4 *>(p.scale + c));
+        if (on && p.shift) sf = __ldg(reinterpret_cast<const float4 *>(p.shift + c));
+        const float *Pj = p.P + dh + (on ? c : 0);
+        const float *Te = p.Te + (on ? c : 0);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pic = pi[0];
+        int cur = 0;
+        int nxt = __shfl_sync(0xffffffffu, rp, 1);
+        for (int base = kb; base < ke; base += 32) {
+            const int n = min(32, ke - base);
+            int jl = 0, tl = 0;
+            if (lane < n) { jl = __ldg(p.nbr + base + lane); tl = __ldg(p.edge_rows + base + lane); }
+            for (int u0 = 0; u0 < n; u0 += U) {
+                float4 pj[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = __shfl_sync(0xffffffffu, jl, (u0 + u) & 31);
+                    if (u0 + u < n) pj[u] = __ldg(reinterpret_cast<const float4 *>(Pj + (int64_t)j * (2 * dh)));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int t = __shfl_sync(0xffffffffu, tl, (u0 + u) & 31);
+                    if (u0 + u < n) {
+                        const float4 te = __ldg(reinterpret_cast<const float4 *>(Te + (int64_t)t * dh));   // L1-resident table row
+                        const int k = base + u0 + u;
+                        while (k >= nxt) {                    // warp-uniform: rows are contiguous in k
+                            if (on) *reinterpret_cast<float4 *>(p.S + (r0 + cur) * dh + c) = acc;
+                            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                            ++cur;
+                            nxt = __shfl_sync(0xffffffffu, rp, cur + 1);
+#pragma unroll
+                            for (int g = 1; g < G; ++g) if (g == cur) pic = pi[g];
+                        }
+                        acc.x += apply_act(fmaf(pic.x + pj[u].x + te.x, sc.x, sf.x), p.act);
+                        acc.y += apply_act(fmaf(pic.y + pj[u].y + te.y, sc.y, sf.y), p.act);
+                        acc.z += apply_act(fmaf(pic.z + pj[u].z + te.z, sc.z, sf.z), p.act);
+                        acc.w += apply_act(fmaf(pic.w + pj[u].w + te.w, sc.w, sf.w), p.act);
+                    }
+                }
+            }
+        }
+        for (; cur < nrows; ++cur) {
+            if (on) *reinterpret_cast<float4 *>(p.S + (r0 + cur) * dh + c) = acc;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 // Lean specialisation for the fully categorical layer (layer 0 of the ZINC / IMDB recipes): no dense operand at
 // all, one node column (atom type) and C edge columns (identifier ranks, bond type), edge rows in CSR order.
 // 32 registers (full occupancy): every term is an L1/L2-resident table row reached through a dependent index load.
@@ -742,6 +926,34 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool v4 = dh % 4 == 0 && aligned16(d_P) && aligned16(d_Q) && aligned16(d_S) && aligned16(d_Tn) && aligned16(d_Te);
     (void)te_rows;
+    const int cpr4 = dh / 4;
+    const bool pow2 = v4 && (cpr4 & (cpr4 - 1)) == 0;
+    int sh = 0;
+    while ((1 << sh) < cpr4) ++sh;
+    // 32-bit element indexing: float4 offsets into P / Tn ([rows, 2dh]), S and the CSR-ordered edge rows
+    const bool tight = pow2 && !d_scale && !d_shift && edge_rows_csr && N * 2 * cpr4 < (int64_t)1 << 31 &&
+                       E * (int64_t)(n_edge_cols > 0 ? n_edge_cols : 1) < (int64_t)1 << 31 &&
+                       (int64_t)te_rows * cpr4 < (int64_t)1 << 31 && !getenv("GSN_NO_TIGHT");
+    if (tight && !d_Q && ((d_P && n_node_cols == 0 && n_edge_cols == 1) || (!d_P && n_node_cols == 1 && n_edge_cols >= 1))) {
+        const uint32_t total = (uint32_t)(N * cpr4);
+        const unsigned grid = (unsigned)ceil_div(total, kMpThreads);
+        const float4 *Te4 = reinterpret_cast<const float4 *>(d_Te);
+        float4 *S4 = reinterpret_cast<float4 *>(d_S);
+        if (d_P) {
+            const float4 *P4 = reinterpret_cast<const float4 *>(d_P);
+            if (act == 0) p1_tight_kernel<0><<<grid, kMpThreads, 0, stream>>>(d_rowptr, d_nbr, d_edge_rows, P4, Te4, S4, total, sh, act);
+            else if (act == 3) p1_tight_kernel<3><<<grid, kMpThreads, 0, stream>>>(d_rowptr, d_nbr, d_edge_rows, P4, Te4, S4, total, sh, act);
+            else p1_tight_kernel<-1><<<grid, kMpThreads, 0, stream>>>(d_rowptr, d_nbr, d_edge_rows, P4, Te4, S4, total, sh, act);
+        } else {
+            const float4 *Tn4 = reinterpret_cast<const float4 *>(d_Tn);
+            if (act == 0) tab_tight_kernel<0><<<grid, kMpThreads, 0, stream>>>(d_rowptr, d_nbr, d_node_rows, d_edge_rows, n_edge_cols, Tn4, Te4, S4, total, sh, act);
+            else if (act == 3) tab_tight_kernel<3><<<grid, kMpThreads, 0, stream>>>(d_rowptr, d_nbr, d_node_rows, d_edge_rows, n_edge_cols, Tn4, Te4, S4, total, sh, act);
+            else tab_tight_kernel<-1><<<grid, kMpThreads, 0, stream>>>(d_rowptr, d_nbr, d_node_rows, d_edge_rows, n_edge_cols, Tn4, Te4, S4, total, sh, act);
+        }
+        GSN_BUMP(1);
+        GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");
+        return GSN_OK;
+    }
     if (v4 && !d_P && !d_Q && n_node_cols == 1 && n_edge_cols >= 1 && edge_rows_csr) {
         general_edge_tab_kernel<4><<<(unsigned)ceil_div(N * (dh / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
         GSN_BUMP(1);
@@ -749,6 +961,31 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
         return GSN_OK;
     }
     if (v4 && d_P && !d_Q && n_node_cols == 0 && n_edge_cols == 1 && edge_rows_csr) {
+        static const int variant = getenv("GSN_P1_VARIANT") ? atoi(getenv("GSN_P1_VARIANT")) : 0;
+        if (variant >= 6) {
+            const unsigned grid = (unsigned)ceil_div(N * (dh / 4), kMpThreads);
+            const bool aff = d_scale || d_shift;
+            const bool regs = te_rows >= 1 && te_rows <= 4 && variant != 6;
+            if (regs && aff) general_edge_p1b_kernel<true, true><<<grid, kMpThreads, 0, stream>>>(p, te_rows);
+            else if (regs) general_edge_p1b_kernel<true, false><<<grid, kMpThreads, 0, stream>>>(p, te_rows);
+            else if (aff) general_edge_p1b_kernel<false, true><<<grid, kMpThreads, 0, stream>>>(p, te_rows);
+            else general_edge_p1b_kernel<false, false><<<grid, kMpThreads, 0, stream>>>(p, te_rows);
+            GSN_BUMP(1);
+            GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");
+            return GSN_OK;
+        }
+        if (variant > 0) {
+            const int G = variant == 1 ? 4 : variant == 2 ? 4 : variant == 3 ? 8 : variant == 4 ? 2 : 8;
+            const unsigned grid = (unsigned)ceil_div(ceil_div(N, G) * 32, kMpThreads);
+            if (variant == 1) general_edge_p1_warp_kernel<4, 4><<<grid, kMpThreads, 0, stream>>>(p);
+            else if (variant == 2) general_edge_p1_warp_kernel<4, 8><<<grid, kMpThreads, 0, stream>>>(p);
+            else if (variant == 3) general_edge_p1_warp_kernel<8, 8><<<grid, kMpThreads, 0, stream>>>(p);
+            else if (variant == 4) general_edge_p1_warp_kernel<2, 4><<<grid, kMpThreads, 0, stream>>>(p);
+            else general_edge_p1_warp_kernel<8, 4><<<grid, kMpThreads, 0, stream>>>(p);
+            GSN_BUMP(1);
+            GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");
+            return GSN_OK;
+        }
         general_edge_p1_kernel<4><<<(unsigned)ceil_div(N * (dh / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
         GSN_BUMP(1);
         GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");

@@ -8,8 +8,9 @@ mode, re-associated so that the whole forward is a handful of library kernels:
     first Linear of msg_fn / update_fn), and one_hot_unique
     (utils_encoding.py:37-59) is a binary search over the sorted vocabulary, so
     raw identifier counts go straight from COUNT into the message kernel;
-  * BatchNorm1d (eval) is a per-channel scale/shift applied in the kernels'
-    epilogues; the second Linear of msg_fn commutes with the neighbour sum and is
+  * BatchNorm1d (eval) is a per-channel scale/shift: applied in the GEMM epilogues of
+    update_fn / the model, folded into the weights and tables of msg_fn's first Linear;
+    the second Linear of msg_fn commutes with the neighbour sum and is
     pre-multiplied into update_fn's first Linear:
         cat(x, sum_e(W2 h_e + b2)) U1^T = x U1x^T + S (U1a W2)^T + deg (U1a b2)
   * per layer: [P GEMM] -> message kernel -> update GEMM -> output GEMM (+ model BN + act).
@@ -77,16 +78,27 @@ class FusedForward:
             d_id = ie.d_out if ie is not None else 0
             d_ef = ee.d_out if ee is not None else 0
             Wxi, Wxj, Wii, Wij, Wq_id, Wq_ef = conv._split_first_linear(d_in, d_id, d_ef)
+            # BatchNorm (eval) of msg_fn + bias of its first Linear: ((P_i + P_j + Q) + b1) * s0 + t0.  The scale is folded
+            # into every block of the first Linear and the shift into the P_i operand (GEMM bias / x-table rows), so the
+            # message kernel is a bare act(P_i + P_j + rows): no per-edge scale / shift traffic on the L1 data pipe.
+            s0, t0 = f.bn_affine(0)
+            b1 = f.fc[0].bias
+            shift = (b1 if s0 is None else b1 * s0 + t0).contiguous()
+            if s0 is not None:
+                Wxi, Wxj, Wii, Wij, Wq_id, Wq_ef = [None if W is None else W * s0[:, None]
+                                                    for W in (Wxi, Wxj, Wii, Wij, Wq_id, Wq_ef)]
             L = {'dh': dh, 'act_mlp': conv.activation_name, 'x_cat': x_cat and i == 0, 'ef_cat': ef_cat,
                  'uses_ids': conv.uses_ids, 'uses_ef': conv.uses_ef, 'local': conv.id_scope == 'local', 'flow': conv.flow}
             # node side of the first Linear
             Wp = torch.cat((Wxi, Wxj), 0).contiguous()                  # [2dh, d_in]
             node_tables = []
             if L['x_cat']:
-                node_tables.append(Wp.t().contiguous())                  # [d_in rows, 2dh]
-                L['Wp'] = None
+                tab = Wp.t().contiguous()                                # [d_in rows, 2dh]; exactly one row per node
+                tab[:, :dh] += shift
+                node_tables.append(tab)
+                L['Wp'], L['bp'] = None, None
             else:
-                L['Wp'] = Wp
+                L['Wp'], L['bp'] = Wp, torch.cat((shift, torch.zeros_like(shift))).contiguous()
             if conv.uses_ids and not L['local']:
                 node_tables.append(torch.cat((Wii, Wij), 0).t().contiguous())   # [d_id rows, 2dh]
             L['Tn'] = torch.cat(node_tables, 0).contiguous() if node_tables else None
@@ -103,13 +115,6 @@ class FusedForward:
                 else:
                     L['Wq_ef'] = Wq_ef.contiguous()
             L['Te'] = torch.cat(edge_tables, 0).contiguous() if edge_tables else None
-            # BatchNorm of msg_fn + bias of its first Linear -> scale / shift
-            s0, t0 = f.bn_affine(0)
-            b1 = f.fc[0].bias
-            if s0 is None:
-                L['scale'], L['shift'] = None, b1.clone()
-            else:
-                L['scale'], L['shift'] = s0.contiguous(), (b1 * s0 + t0).contiguous()
             # update_fn with the second message Linear folded in
             W2, b2 = f.fc[1].weight, f.fc[1].bias
             U1, c1 = u.fc[0].weight, u.fc[0].bias
@@ -222,13 +227,13 @@ class FusedForward:
                 if only_ef:
                     ef_rows_cache[key] = edge_rows
             # ---- dense parts
-            P = ops.linear(x, L['Wp']) if L['Wp'] is not None else None
+            P = ops.linear(x, L['Wp'], bias=L['bp']) if L['Wp'] is not None else None
             Q = None
             if L['uses_ef'] and not L['ef_cat']:
                 ee = m.edge_encoder[i if m.inject_edge_features else 0]
                 Q = ops.linear(ee(data.edge_features).contiguous(), L['Wq_ef'])
             S = ops.general_edge_idx(plan, dh, P=P, Q=Q, node_rows=node_rows, Tn=L['Tn'], edge_rows=edge_rows,
-                                     Te=L['Te'], scale=L['scale'], shift=L['shift'], activation=L['act_mlp'],
+                                     Te=L['Te'], activation=L['act_mlp'],
                                      edge_rows_csr=True)
             # ---- update_fn (first Linear carries the folded second message Linear) + BN + act
             if L['x_cat']:
