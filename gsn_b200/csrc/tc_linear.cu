@@ -29,6 +29,7 @@ struct TcEpilogue {
     float *C;
     int M, Nout, K, ldc, tab_ld, act, accumulate;
     long long *dbg;          // optional [grid, 8] clock64 stamps (profiling aid)
+    int mode;                // experiment switches (GSN_TC_MODE): 1 skip epilogue, 2 skip MMA, 4 skip split
 };
 
 // elu / tanh are kept out of line: inlining them into the unrolled epilogue makes it tens of KB of straight-line
@@ -328,6 +329,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(512, 1)
 tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                             const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                            const __grid_constant__ CUtensorMap tmC,
                             const __grid_constant__ TcEpilogue ep, int K1, int m_tiles, int n_tiles) {
     constexpr int A_TILE = TC_BM * TC_BK * 4;
     constexpr int W_TILE = BN * TC_BK * 4;
@@ -340,8 +342,11 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
     const int nk = (ep.K + TC_BK - 1) / TC_BK;
     const int total_tiles = m_tiles * n_tiles;
     unsigned char *ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    unsigned char *stage_out = ring + (size_t)STAGES * STAGE;                        // 4 epilogue warps x 4 KB, 1024-aligned
+    float *col_const = reinterpret_cast<float *>(stage_out + 4 * 4096);              // [3][BN]: scale | bias*scale+shift | vec*scale
 
     if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_hi) : "memory");
@@ -409,6 +414,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
                 for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
                     const uint32_t first = (kt > 0 || k > 0) ? 1u : 0u;
+                    if (ep.mode & 2) continue;
                     umma_tf32(acc_main, a_hi + adv, w_hi + adv, idesc, first);
                     umma_tf32(acc_corr, a_lo + adv, w_hi + adv, idesc, first);
                     umma_tf32(acc_corr, a_hi + adv, w_lo + adv, idesc, 1u);
@@ -432,6 +438,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
                 float4 av[NV];
 #pragma unroll
                 for (int i = 0; i < NV; ++i) av[i] = hi[tid + i * 256];
+                if (!(ep.mode & 4))
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     const float4 a = av[i];
@@ -454,25 +461,49 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
             }
         }
     } else if (warp >= 12) {
-        // ---------------- epilogue: one output row per thread, all BN columns
+        // ---------------- epilogue.  Thread = output row (TMEM lane), 32 columns per pass.  The per-column operands are
+        // folded once per n-tile into three shared-memory vectors (broadcast LDS instead of 4 predicated LDG per
+        // element), the finished 32 x 32 block is written to a SWIZZLE_128B staging buffer owned by this warp and
+        // leaves through a TMA store (or reduce-add for `accumulate`): full-line writes, no strided 16-byte stores,
+        // ragged M / Nout clipped by the tensor map.  Measured before this rewrite: the epilogue bounded the kernel
+        // (1188 us with it, 519 us without, M = 3.04 M, K = N = 128).
         const int wq = warp & 3;
+        const int te = threadIdx.x - 384;                     // 0..127 among the epilogue threads
         const bool accumulate = ep.accumulate == 1;
         const int act = ep.act;
-        const float *bias = ep.bias, *row_vec = ep.row_vec, *scale = ep.scale, *shift = ep.shift;
-        const bool vec = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
-        int tc = 0;
+        unsigned char *stg = stage_out + wq * 4096;
+        const uint32_t stg_row = smem_u32(stg) + (uint32_t)lane * 128u;
+        float *cS = col_const, *cB = col_const + BN, *cV = col_const + 2 * BN;
+        int tc = 0, staged_n0 = -1;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
             const int b = tc & 1;
             const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+            if (n0 != staged_n0) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = te; c < BN; c += 128) {
+                    const int col = n0 + c;
+                    const bool ok = col < ep.Nout;
+                    const float sc = (ok && ep.scale) ? __ldg(ep.scale + col) : 1.f;
+                    const float bi = (ok && ep.bias) ? __ldg(ep.bias + col) : 0.f;
+                    const float sf = (ok && ep.shift) ? __ldg(ep.shift + col) : 0.f;
+                    const float rv = (ok && ep.row_vec) ? __ldg(ep.row_vec + col) : 0.f;
+                    cS[c] = sc;
+                    cB[c] = fmaf(bi, sc, sf);
+                    cV[c] = rv * sc;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                staged_n0 = n0;
+            }
             mbar_wait(&tmem_full_bar[b], (tc >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int m = m0 + wq * 32 + lane;
             const bool mok = m < ep.M;
             const float rs = (ep.row_scale && mok) ? __ldg(ep.row_scale + m) : 0.f;
             const float *trow = (ep.tab && mok) ? ep.tab + (int64_t)__ldg(ep.tab_idx + m) * ep.tab_ld : nullptr;
-            float *crow = ep.C + (int64_t)(mok ? m : 0) * ep.ldc;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int nb = n0 + c0;
+                if (nb >= ep.Nout || (ep.mode & 1)) break;            // warp-uniform
                 uint32_t r[32], q[32];
                 const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * 2 * BN + c0);
                 asm volatile(
@@ -496,53 +527,62 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int nb = n0 + c0;
-                if (mok && nb < ep.Nout) {
-                    float v[32];
+                float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(q[j]);
-                    const bool whole = nb + 32 <= ep.Nout;
-                    if (row_vec) {
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(q[j]);
+                if (trow) {
+                    if (nb + 32 <= ep.Nout && (ep.tab_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.tab) & 15) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, (whole || nb + j < ep.Nout) ? __ldg(row_vec + nb + j) : 0.f, v[j]);
-                    }
-                    if (trow) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += (whole || nb + j < ep.Nout) ? __ldg(trow + nb + j) : 0.f;
-                    }
-                    if (bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += (whole || nb + j < ep.Nout) ? __ldg(bias + nb + j) : 0.f;
-                    }
-                    if (scale) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= (whole || nb + j < ep.Nout) ? __ldg(scale + nb + j) : 1.f;
-                    }
-                    if (shift) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += (whole || nb + j < ep.Nout) ? __ldg(shift + nb + j) : 0.f;
-                    }
-                    if (act == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (act != 3) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = tc_act_slow(v[j], act);
-                    }
-                    if (accumulate) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (whole || nb + j < ep.Nout) v[j] += crow[nb + j];
-                    }
-                    if (vec && whole) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 tv = __ldg(reinterpret_cast<const float4 *>(trow + nb + j));
+                            v[j] += tv.x; v[j + 1] += tv.y; v[j + 2] += tv.z; v[j + 3] += tv.w;
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (nb + j < ep.Nout) crow[nb + j] = v[j];
+                        for (int j = 0; j < 32; ++j) v[j] += (nb + j < ep.Nout) ? __ldg(trow + nb + j) : 0.f;
                     }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 s4 = *reinterpret_cast<const float4 *>(cS + c0 + j);
+                    const float4 b4 = *reinterpret_cast<const float4 *>(cB + c0 + j);
+                    v[j] = fmaf(v[j], s4.x, b4.x); v[j + 1] = fmaf(v[j + 1], s4.y, b4.y);
+                    v[j + 2] = fmaf(v[j + 2], s4.z, b4.z); v[j + 3] = fmaf(v[j + 3], s4.w, b4.w);
+                }
+                if (ep.row_vec) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 v4 = *reinterpret_cast<const float4 *>(cV + c0 + j);
+                        v[j] = fmaf(rs, v4.x, v[j]); v[j + 1] = fmaf(rs, v4.y, v[j + 1]);
+                        v[j + 2] = fmaf(rs, v4.z, v[j + 2]); v[j + 3] = fmaf(rs, v4.w, v[j + 3]);
+                    }
+                }
+                if (act == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (act != 3) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = tc_act_slow(v[j], act);
+                }
+                // the previous TMA store of this warp must have finished READING the staging buffer
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const uint32_t addr = stg_row + (uint32_t)((j4 ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j4]), "f"(v[4 * j4 + 1]),
+                                 "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (accumulate)
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&tmC), "r"(nb), "r"(m0 + wq * 32), "r"(smem_u32(stg)) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&tmC), "r"(nb), "r"(m0 + wq * 32), "r"(smem_u32(stg)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
             // this warp is done reading accumulator buffer b: hand it back to the MMA warp
@@ -550,6 +590,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[b])) : "memory");
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -641,8 +682,9 @@ static int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUt
 
 template <int BN, int STAGES>
 static int launch_tc_persistent(const CUtensorMap &a1, const CUtensorMap &a2, const CUtensorMap &w_hi, const CUtensorMap &w_lo,
-                                const TcEpilogue &ep, int K1, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024;
+                                const CUtensorMap &c_map, const TcEpilogue &ep, int K1, cudaStream_t stream) {
+    // ring | 4 x 4 KB store staging | 3 x BN column constants | alignment slack
+    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 4 * 4096 + 3 * BN * 4 + 1024;
     static bool attr = false;
     if (!attr) {
         GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -651,7 +693,7 @@ static int launch_tc_persistent(const CUtensorMap &a1, const CUtensorMap &a2, co
     const int m_tiles = (int)ceil_div(ep.M, TC_BM), n_tiles = (int)ceil_div(ep.Nout, BN);
     const int64_t total = (int64_t)m_tiles * n_tiles;
     const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
-    tc_linear_persistent_kernel<BN, STAGES><<<grid, 512, smem, stream>>>(a1, a2, w_hi, w_lo, ep, K1, m_tiles, n_tiles);
+    tc_linear_persistent_kernel<BN, STAGES><<<grid, 512, smem, stream>>>(a1, a2, w_hi, w_lo, c_map, ep, K1, m_tiles, n_tiles);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("tc_linear_persistent_kernel");
     return GSN_OK;
@@ -697,7 +739,8 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
     const int64_t m_tiles = ceil_div(p.M, TC_BM);
     if (m_tiles * ceil_div(p.Nout, BN) < kNumSMs / 2 && p.Nout >= 32) BN = 32;
     TcEpilogue ep{p.bias, p.row_scale, p.row_vec, p.tab, p.scale, p.shift, p.tab_idx, p.C,
-                  p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate, (long long *)g_tc_debug};
+                  p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate, (long long *)g_tc_debug,
+                  getenv("GSN_TC_MODE") ? atoi(getenv("GSN_TC_MODE")) : 0};
     CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
     int rc;
     if ((rc = make_map(&mW_hi, d_Whi, p.Nout, K, K, BN))) return rc;
@@ -710,13 +753,15 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
         else mA_lo = mA_hi;
         // large problems: persistent kernel (continuous ring, double-buffered TMEM accumulators)
         const int BNp = p.Nout > 64 ? 128 : 64;
-        if (!g_tc_no_persistent && m_tiles * ceil_div(p.Nout, BNp) >= 2 * kNumSMs) {
+        if (!g_tc_no_persistent && m_tiles * ceil_div(p.Nout, BNp) >= 2 * kNumSMs && p.ldc % 4 == 0 && al16(p.C)) {
+            CUtensorMap mC;                       // output tile store: box = 32 rows x 32 columns (128 B), swizzled
+            if ((rc = make_map(&mC, p.C, p.M, p.Nout, p.ldc, 32))) return rc;
             if (BNp != BN) {
                 if ((rc = make_map(&mW_hi, d_Whi, p.Nout, K, K, BNp))) return rc;
                 if ((rc = make_map(&mW_lo, d_Wlo, p.Nout, K, K, BNp))) return rc;
             }
-            if (BNp == 128) return launch_tc_persistent<128, 3>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
-            return launch_tc_persistent<64, 4>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
+            if (BNp == 128) return launch_tc_persistent<128, 3>(mA_hi, mA_lo, mW_hi, mW_lo, mC, ep, p.K1, stream);
+            return launch_tc_persistent<64, 4>(mA_hi, mA_lo, mW_hi, mW_lo, mC, ep, p.K1, stream);
         }
         if (BN == 32) return launch_tc<32, 5, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
         if (BN == 256) return launch_tc<256, 2, true>(mA_hi, mA_lo, mW_hi, mW_lo, ep, p.K1, stream);
