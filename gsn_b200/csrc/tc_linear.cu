@@ -380,6 +380,22 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+            // The ring holds 3-4 k-steps (48 KB of DRAM reads in flight per SM); under load an HBM round trip is ~3 k
+            // cycles, i.e. ~1.5 k cycles per k-step against 768 of MMA work.  The activation rows of this CTA's NEXT
+            // tile are therefore pulled into L2 now (no shared memory needed), one whole tile ahead.
+            if (!(ep.mode & 8)) {
+                const int tn = t + (int)gridDim.x;
+                if (tn < total_tiles) {
+                    const int mn = (tn / n_tiles) * TC_BM;
+                    for (int kt = 0; kt < nk; ++kt) {
+                        const int k0 = kt * TC_BK;
+                        if (k0 < K1)
+                            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmA1), "r"(k0), "r"(mn) : "memory");
+                        else
+                            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmA2), "r"(k0 - K1), "r"(mn) : "memory");
+                    }
+                }
+            }
             for (int kt = 0; kt < nk; ++kt, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
