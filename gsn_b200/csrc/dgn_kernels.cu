@@ -1,0 +1,182 @@
+// Directional aggregation of the DGN consumer of COUNT.
+//
+// Replaces DGNLayerSimple.pretrans_edges / message_func / reduce_func of the reference
+// (directional_gsn/nets/dgn_layer.py:28-54) together with the aggregator and scaler
+// functions it dispatches to (directional_gsn/nets/aggregators.py:8-69, nets/scalers.py:7-20):
+// DGL builds a mailbox [n, D, d] per in-degree bucket D, evaluates every aggregator on it
+// as a separate chain of torch ops and concatenates; the "vector field" of an edge is
+// eig[src] - eig[dst] (node fields, i.e. vertex-scope substructure counts) followed by the
+// edge fields (edge-scope counts) -- data/HIV.py:91-98.
+//
+// Here: the in-edges of a node come from the same CSR the message-passing kernels use
+// (ascending edge id inside a row = DGL's mailbox order), one thread owns one (node,
+// 4-channel chunk) and produces every aggregator x scaler block of the output row.  The
+// per-edge weights of the directional aggregators depend only on the fields, so they are
+// computed once per aggregator and applied while h_j streams through L1; nothing of size
+// [E, d] or [n, D, d] is materialised.
+#include "common.cuh"
+
+namespace gsn {
+
+constexpr float kDgnEps = 1e-8f;      // aggregators.py:5
+
+struct DgnParams {
+    const int32_t *rowptr, *eid, *nbr;
+    int64_t N;
+    const float *h, *node_field, *edge_field;
+    int d, Fn, Fe, n_aggr, n_scalers;
+    int aggr_kind[GSN_DGN_MAX_AGGR], aggr_idx[GSN_DGN_MAX_AGGR];
+    float aggr_alpha[GSN_DGN_MAX_AGGR];
+    int scaler_kind[GSN_DGN_MAX_SCALERS];
+    float avg_log;
+    float *out;
+};
+
+template <int VEC> __device__ __forceinline__ void ld_vec(const float *src, float (&dst)[VEC]) {
+    if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(src));
+        dst[0] = t.x; dst[1 % VEC] = t.y; dst[2 % VEC] = t.z; dst[3 % VEC] = t.w;
+    } else {
+        dst[0] = __ldg(src);
+    }
+}
+
+// component `f` of the vector field of CSR position k (in-edge j -> i): dgn_layer.py:28-35
+__device__ __forceinline__ float dgn_field(const DgnParams &p, int f, int64_t i, int j, int k) {
+    if (f < p.Fn) return __ldg(p.node_field + (int64_t)j * p.Fn + f) - __ldg(p.node_field + i * p.Fn + f);
+    return __ldg(p.edge_field + (int64_t)__ldg(p.eid + k) * p.Fe + (f - p.Fn));
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) dgn_aggregate_kernel(const __grid_constant__ DgnParams p) {
+    const int d = p.d, cpr = d / VEC;
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t i = t / cpr;
+    const int c = (int)(t % cpr) * VEC;
+    const int k0 = __ldg(p.rowptr + i), k1 = __ldg(p.rowptr + i + 1);
+    const int D = k1 - k0;
+    const int AD = p.n_aggr * d;
+    float *orow = p.out + i * (int64_t)(AD * p.n_scalers);
+    // scaler factors (scalers.py:7-20); applied only when more than one scaler is listed (dgn_layer.py:50-51)
+    float sfac[GSN_DGN_MAX_SCALERS];
+    for (int s = 0; s < p.n_scalers; ++s) {
+        float f = 1.0f;
+        if (p.n_scalers > 1 && D > 0) {
+            const double lg = log((double)D + 1.0);
+            if (p.scaler_kind[s] == 1) f = (float)(lg / (double)p.avg_log);
+            else if (p.scaler_kind[s] == 2) f = (float)((double)p.avg_log / lg);
+        }
+        sfac[s] = f;
+    }
+    float hin[VEC];
+    ld_vec<VEC>(p.h + i * d + c, hin);
+    for (int a = 0; a < p.n_aggr; ++a) {
+        const int kind = p.aggr_kind[a], fi = p.aggr_idx[a];
+        float r[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = 0.f;
+        if (D > 0) {
+            if (kind <= GSN_DGN_VAR) {
+                float s1[VEC], s2[VEC], mx[VEC], mn[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { s1[v] = 0.f; s2[v] = 0.f; mx[v] = -INFINITY; mn[v] = INFINITY; }
+                for (int k = k0; k < k1; ++k) {
+                    float xs[VEC];
+                    ld_vec<VEC>(p.h + (int64_t)__ldg(p.nbr + k) * d + c, xs);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const float x = xs[v];
+                        s1[v] += x; s2[v] = __fadd_rn(s2[v], __fmul_rn(x, x)); mx[v] = fmaxf(mx[v], x); mn[v] = fminf(mn[v], x);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    // separately rounded products, as the reference's chain of torch ops (aggregators.py:24-28): an
+                    // fma here would turn the exact zero of a one-message mailbox into the rounding error of h*h,
+                    // which sqrt(var + 1e-8) amplifies to ~1e-4
+                    const float mean = __fdiv_rn(s1[v], (float)D);
+                    const float var = fmaxf(__fsub_rn(__fdiv_rn(s2[v], (float)D), __fmul_rn(mean, mean)), 0.f);
+                    r[v] = kind == GSN_DGN_MEAN ? mean : kind == GSN_DGN_SUM ? s1[v] : kind == GSN_DGN_MAX ? mx[v]
+                         : kind == GSN_DGN_MIN ? mn[v] : kind == GSN_DGN_STD ? sqrtf(var + kDgnEps) : var;
+                }
+            } else {
+                // directional: weights from field component fi
+                float n_abs = 0.f, n_pos = 0.f, n_neg = 0.f, mxs = -INFINITY;
+                for (int k = k0; k < k1; ++k) {
+                    const float F = dgn_field(p, fi, i, __ldg(p.nbr + k), k);
+                    n_abs += fabsf(F); n_pos += fmaxf(F, 0.f); n_neg += fmaxf(-F, 0.f);
+                    mxs = fmaxf(mxs, p.aggr_alpha[a] * fabsf(F));
+                }
+                float se = 0.f;
+                if (kind == GSN_DGN_DIR_SOFTMAX)
+                    for (int k = k0; k < k1; ++k)
+                        se += expf(p.aggr_alpha[a] * fabsf(dgn_field(p, fi, i, __ldg(p.nbr + k), k)) - mxs);
+                float wsum = 0.f;
+                for (int k = k0; k < k1; ++k) {
+                    const int j = __ldg(p.nbr + k);
+                    const float F = dgn_field(p, fi, i, j, k);
+                    float w;
+                    if (kind == GSN_DGN_DIR_AV) w = fabsf(F) / (n_abs + kDgnEps);
+                    else if (kind == GSN_DGN_DIR_SOFTMAX) w = expf(p.aggr_alpha[a] * fabsf(F) - mxs) / se;
+                    else if (kind == GSN_DGN_DIR_DX_BALANCED)
+                        w = (fmaxf(F, 0.f) / (n_pos + kDgnEps) + fmaxf(-F, 0.f) / (n_neg + kDgnEps)) / 2.0f;
+                    else w = F / (n_abs + kDgnEps);
+                    wsum += w;
+                    float xs[VEC];
+                    ld_vec<VEC>(p.h + (int64_t)j * d + c, xs);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) r[v] += xs[v] * w;
+                }
+                if (kind == GSN_DGN_DIR_DX || kind == GSN_DGN_DIR_DX_BALANCED) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) r[v] = fabsf(r[v] - wsum * hin[v]);
+                } else if (kind == GSN_DGN_DIR_DX_NO_ABS) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) r[v] = r[v] - wsum * hin[v];
+                }
+            }
+        }
+        for (int s = 0; s < p.n_scalers; ++s) {
+            float *o = orow + s * AD + a * d + c;
+            if (VEC == 4) *reinterpret_cast<float4 *>(o) = make_float4(r[0] * sfac[s], r[1 % VEC] * sfac[s], r[2 % VEC] * sfac[s], r[3 % VEC] * sfac[s]);
+            else o[0] = r[0] * sfac[s];
+        }
+    }
+}
+
+}  // namespace gsn
+
+using namespace gsn;
+
+extern "C" int gsn_dgn_aggregate_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                                     int64_t E, const float *d_h, int32_t d, const float *d_node_field, int32_t Fn,
+                                     const float *d_edge_field, int32_t Fe, const GsnDgnAggr *h_aggr, int32_t n_aggr,
+                                     const int32_t *h_scalers, int32_t n_scalers, float avg_log, float *d_out,
+                                     void *stream_) {
+    if (N < 0 || E < 0 || d < 1 || !d_rowptr || !d_h || !d_out || !h_aggr || n_aggr < 1 || n_aggr > GSN_DGN_MAX_AGGR ||
+        n_scalers < 1 || n_scalers > GSN_DGN_MAX_SCALERS || !h_scalers || Fn < 0 || Fe < 0)
+        return GSN_E_INVALID;
+    if ((Fn > 0 && !d_node_field) || (Fe > 0 && (!d_edge_field || !d_eid)) || (E > 0 && !d_nbr)) return GSN_E_INVALID;
+    DgnParams p;
+    p.rowptr = d_rowptr; p.eid = d_eid; p.nbr = d_nbr; p.N = N; p.h = d_h; p.node_field = d_node_field;
+    p.edge_field = d_edge_field; p.d = d; p.Fn = Fn; p.Fe = Fe; p.n_aggr = n_aggr; p.n_scalers = n_scalers;
+    p.avg_log = avg_log; p.out = d_out;
+    for (int a = 0; a < n_aggr; ++a) {
+        const GsnDgnAggr &g = h_aggr[a];
+        if (g.kind < GSN_DGN_MEAN || g.kind > GSN_DGN_DIR_DX_BALANCED) return GSN_E_INVALID;
+        if (g.kind >= GSN_DGN_DIR_AV && (g.field < 0 || g.field >= Fn + Fe)) return GSN_E_INVALID;   // reference: IndexError
+        p.aggr_kind[a] = g.kind; p.aggr_idx[a] = g.field; p.aggr_alpha[a] = g.alpha;
+    }
+    for (int s = 0; s < n_scalers; ++s) {
+        if (h_scalers[s] < 0 || h_scalers[s] > 2) return GSN_E_INVALID;
+        p.scaler_kind[s] = h_scalers[s];
+    }
+    if (N == 0) return GSN_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (d % 4 == 0) dgn_aggregate_kernel<4><<<(unsigned)ceil_div(N * (d / 4), 256), 256, 0, stream>>>(p);
+    else dgn_aggregate_kernel<1><<<(unsigned)ceil_div(N * (int64_t)d, 256), 256, 0, stream>>>(p);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_dgn_aggregate_fwd");
+    return GSN_OK;
+}

@@ -304,6 +304,45 @@ int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_t *d_eid, c
  * d_perm = d_eid), which removes one dependent load per edge; 0: indexed by edge_index column. */
 
 /* ------------------------------------------------------------------ */
+/* DGN consumer of COUNT (directional_gsn/)                            */
+/* ------------------------------------------------------------------ */
+/*
+ * Replaces DGNLayerSimple.pretrans_edges / message_func / reduce_func (directional_gsn/nets/dgn_layer.py:28-54), the
+ * aggregators of nets/aggregators.py:8-69 and the scalers of nets/scalers.py:7-20 (DGL mailboxes per in-degree bucket,
+ * one chain of torch ops per aggregator).  CSR from gsn_csr_build over key = edge_index[1] (messages flow src -> dst).
+ *   vector_field(e = j->i) = [ node_field[j,:] - node_field[i,:]  |  edge_field[e,:] ]      (dgn_layer.py:28-35)
+ *   out[i, s*(A*d) + a*d + c] = scaler_s( aggregator_a( {h[j,c]}, vector_field, h[i,c] ) )
+ * Nodes without in-edges get zeros (DGL leaves rows that receive no message zero-filled).  With n_scalers == 1 no
+ * scaling is applied whatever the scaler is (dgn_layer.py:50-51).  avg_log = avg_d["log"] of the training set.
+ */
+#define GSN_DGN_MEAN 0
+#define GSN_DGN_SUM 1
+#define GSN_DGN_MAX 2
+#define GSN_DGN_MIN 3
+#define GSN_DGN_STD 4
+#define GSN_DGN_VAR 5
+#define GSN_DGN_DIR_AV 6            /* dir{k}-av        aggregators.py:35-39 */
+#define GSN_DGN_DIR_SOFTMAX 7       /* dir{k}-{alpha}   aggregators.py:42-45 */
+#define GSN_DGN_DIR_DX 8            /* dir{k}-dx        aggregators.py:48-52 */
+#define GSN_DGN_DIR_DX_NO_ABS 9     /* aggregators.py:55-59 */
+#define GSN_DGN_DIR_DX_BALANCED 10  /* aggregators.py:62-71 */
+#define GSN_DGN_SCALE_IDENTITY 0
+#define GSN_DGN_SCALE_AMPLIFICATION 1
+#define GSN_DGN_SCALE_ATTENUATION 2
+#define GSN_DGN_MAX_AGGR 16
+#define GSN_DGN_MAX_SCALERS 3
+typedef struct GsnDgnAggr {
+    int32_t kind;    /* GSN_DGN_* */
+    int32_t field;   /* eig_idx: component of the vector field (directional kinds) */
+    float alpha;     /* softmax temperature (GSN_DGN_DIR_SOFTMAX) */
+    int32_t _pad;
+} GsnDgnAggr;
+int gsn_dgn_aggregate_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N, int64_t E,
+                          const float *d_h, int32_t d, const float *d_node_field, int32_t Fn, const float *d_edge_field,
+                          int32_t Fe, const GsnDgnAggr *h_aggr, int32_t n_aggr, const int32_t *h_scalers,
+                          int32_t n_scalers, float avg_log, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------ */
 /* misc                                                                */
 /* ------------------------------------------------------------------ */
 int gsn_abi_version(void);
