@@ -1,0 +1,165 @@
+"""BASELINE config 3: ogbg-molhiv recipe (README.md:121) -- GSN-v, graphlets k<=5 (induced, vertex scope: 29 patterns,
+72 orbit columns), GNN_OGB with GSN_edge_sparse_ogb layers (5 layers, width 300, hidden 600, virtual node, dropout 0.5),
+B = 512 synthetic molhiv-shaped graphs: COUNT time and one TRAINING step (forward + backward + Adam).
+
+    python scripts/bench_ogb.py                    # this package on cuda:0
+    python scripts/bench_ogb.py --impl reference   # the unmodified reference model on the host CPU (needs /root/reference)
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+sys.path.insert(0, ROOT)
+ATOM, BOND = [119, 4, 12, 12, 10, 6, 6, 2, 2], [5, 6, 2]
+
+
+def graphlets():
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'graphlets.npz'))
+    out = []
+    for k in (3, 4, 5):
+        ptr, ed = z[f'k{k}_ptr'], z[f'k{k}_edges']
+        out += [ed[ptr[i]:ptr[i + 1]].tolist() for i in range(len(ptr) - 1)]
+    return out
+
+
+def model_args(L, d, dh, dropout):
+    return dict(seed=0, model_name='GSN_edge_sparse_ogb', readout='mean', dropout_features=[dropout] * (L + 1),
+                bn=[True] * L, final_projection=[False] * L + [True], residual=False, inject_ids=False,
+                inject_edge_features=True, vn=True, vn_pooling='sum', input_vn_encoder='embedding',
+                d_out_vn_encoder=d, d_out_vn=[d] * (L - 1), id_scope='global', d_msg=[d] * L, d_out=[d] * L,
+                d_h=[[dh]] * L, aggr='add', flow='source_to_target', msg_kind='ogb', train_eps=[False] * L,
+                activation_mlp='relu', bn_mlp=True, jk_mlp=False, degree_embedding='one_hot_encoder',
+                degree_as_tag=[False] * L, retain_features=[False] + [True] * (L - 1), multi_embedding_aggr='sum',
+                features_scope='full', input_node_encoder='atom_encoder', d_out_node_encoder=d,
+                edge_encoder='bond_encoder', d_out_edge_encoder=[d] * L, id_embedding='embedding',
+                d_out_id_embedding=d, d_out_degree_embedding=d, extend_dims=True, activation='relu')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--batch', type=int, default=512)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--id-cap', type=int, default=64, help='identifier embedding rows per column (counts are clamped)')
+    a = ap.parse_args()
+    from gsn_b200.synthetic import zinc_like_batch
+    b = zinc_like_batch(a.batch, seed=21, mean_nodes=25.5, sd_nodes=12.0, min_nodes=2, max_nodes=222)
+    N, E = int(b['node_ptr'][-1]), int(b['edge_index'].shape[1])
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(np.stack([rng.integers(0, d, N) for d in ATOM], 1))
+    ef = torch.from_numpy(np.stack([rng.integers(0, d, E) for d in BOND], 1))
+    y = torch.from_numpy(rng.integers(0, 2, (a.batch, 1))).float()
+    ei, node_ptr = torch.from_numpy(b['edge_index']), torch.from_numpy(b['node_ptr'])
+    els = graphlets()
+    L, d, dh = 5, 300, 600
+    args = model_args(L, d, dh, 0.5)
+    res = {'config': f'molhiv-shaped synthetic batch B={a.batch} (N={N}, E={E}); all_simple_graphs k<=5 induced, id_scope '
+                     f'global ({len(els)} patterns); GNN_OGB + GSN_edge_sparse_ogb, {L} layers, d_out {d}, d_h {dh}, vn, '
+                     'dropout 0.5; train step = forward + BCE + backward + Adam', 'impl': a.impl, 'steps': a.steps}
+
+    class Obj:
+        pass
+
+    if a.impl == 'ours':
+        from gsn_b200 import counting, patterns
+        from gsn_b200.network import GNN_OGB
+        dev = torch.device('cuda', 0)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        sds = patterns.make_subgraph_dicts(els, 'global')
+        ei_d = ei.to(dev)
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            ids = counting.count_batch(ei_d, node_ptr, sds, True, 'global')
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(5):
+            ids = counting.count_batch(ei_d, node_ptr, sds, True, 'global')
+        e1.record()
+        torch.cuda.synchronize()
+        res['count_ms'] = e0.elapsed_time(e1) / 5
+        res['id_columns'] = int(ids.shape[1])
+        ids = ids.clamp_max(a.id_cap - 1)
+        ctor = dict(in_features=9, out_features=1, encoder_ids=None, d_in_id=[a.id_cap] * ids.shape[1], in_edge_features=3,
+                    d_in_node_encoder=None, d_in_edge_encoder=None, encoder_degrees=None, d_degree=None)
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = GNN_OGB(**ctor, **args).to(dev).train()
+        data = Obj()
+        data.edge_index, data.batch, data.x, data.edge_features = ei_d, torch.from_numpy(b['batch']).to(dev), x.to(dev), ef.to(dev)
+        data.identifiers, data.degrees, data.node_ptr = ids, torch.from_numpy(b['degrees']).to(dev), node_ptr.to(dev)
+        yd = y.to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(model(data), yd)
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(a.warmup):
+            step()
+        torch.cuda.synchronize()
+        from gsn_b200 import _lib
+        l0 = _lib.launch_count()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(a.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        res.update(train_step_ms=ms, graphs_per_s=a.batch / (ms * 1e-3), loss=float(loss),
+                   gsn_kernel_launches_per_step=(_lib.launch_count() - l0) / a.steps,
+                   count_plus_step_graphs_per_s=a.batch / ((ms + res['count_ms']) * 1e-3))
+        model.eval()
+        with torch.no_grad():
+            for _ in range(2):
+                model(data)
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(a.steps):
+                model(data)
+            e1.record()
+            torch.cuda.synchronize()
+        res['eval_forward_ms'] = e0.elapsed_time(e1) / a.steps
+    else:
+        from oracle import ref_import
+        M = ref_import.models()
+        ids = torch.from_numpy(rng.integers(0, a.id_cap, (N, 72)))      # counting is not timed here (graph-tool absent)
+        ctor = dict(in_features=9, out_features=1, encoder_ids=None, d_in_id=[a.id_cap] * 72, in_edge_features=3,
+                    d_in_node_encoder=None, d_in_edge_encoder=None, encoder_degrees=None, d_degree=None)
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = M['GNN_OGB'](**ctor, **args).train()
+        data = Obj()
+        data.edge_index, data.batch, data.x, data.edge_features = ei, torch.from_numpy(b['batch']), x, ef
+        data.identifiers, data.degrees = ids, torch.from_numpy(b['degrees'])
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        ts = []
+        for i in range(1 + min(a.steps, 3)):
+            t0 = time.perf_counter()
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(model(data), y)
+            loss.backward()
+            opt.step()
+            ts.append(time.perf_counter() - t0)
+        ms = float(np.median(ts[1:])) * 1e3
+        res.update(train_step_ms=ms, graphs_per_s=a.batch / (ms * 1e-3), cores=torch.get_num_threads(),
+                   note='unmodified reference model (models_graph_classification_ogb_original.py) on the host CPU, PyTorch '
+                        'threads = cores; identifiers random (graph-tool absent, COUNT not timed)')
+    print(json.dumps(res))
+
+
+if __name__ == '__main__':
+    main()
