@@ -259,16 +259,19 @@ def run_ours(args, rank, world, local_rank):
         prof = instrumented(dev_in, max(3, min(args.steps, 10)))
         dh = D_OUT
 
+        from gsn_b200.fused import MERGE_MAX_ROWS, _merge_edge_columns
         n_id_cols = len(encoder.d)
+        # index columns the layer-0 message kernel reads per edge after column grouping (fused.py)
+        n_l0_cols = _merge_edge_columns(torch.zeros((sum(encoder.d) + 4, 1)), _edge_cols(encoder), MERGE_MAX_ROWS)[1]['n_groups']
 
         def scatter_bytes(n, e):
             """algorithmic bytes of ONE launch of the message (scatter) kernel, averaged over the N_LAYERS launches
-            of a step.  Layer 0 reads only indices (x: 4 B/node, identifiers + bond type:
-            4 B x (id columns + 1) per edge); layers >= 1 read P [N, 2dh] fp32 and one 4-byte index per edge.
+            of a step.  Layer 0 reads only indices (x: 4 B/node, identifiers + bond type folded
+            into n_l0_cols grouped row indices of 4 B per edge); layers >= 1 read P [N, 2dh] fp32 and one 4-byte index per edge.
             Every launch reads the CSR (rowptr + nbr, 4 B each) and writes S [N, dh] fp32."""
             csr = 4 * e + 4 * (n + 1)
             out = 4 * dh * n
-            layer0 = 4 * n + 4 * (n_id_cols + 1) * e + csr + out
+            layer0 = 4 * n + 4 * n_l0_cols * e + csr + out
             later = 4 * 2 * dh * n + 4 * e + csr + out
             return (layer0 + (N_LAYERS - 1) * later) / N_LAYERS
         # device duration of the message kernel at the step's own shapes: R back-to-back launches inside one event
@@ -370,6 +373,15 @@ def run_ours(args, rank, world, local_rank):
     return line
 
 
+def _edge_cols(encoder):
+    """(vocabulary size, first table row) of the layer-0 edge columns: identifier ranks, then the bond type"""
+    cols, o = [], 0
+    for d in list(encoder.d) + [4]:
+        cols.append((int(d), o))
+        o += int(d)
+    return cols
+
+
 def scatter_launch_seconds(dev, batch, encoder, reps, flush=None):
     """mean device seconds of ONE message-kernel launch of a step on `batch` (weights: 1 layer-0 launch reading only
     indices + (N_LAYERS-1) launches reading P and one index column), timed as back-to-back launches"""
@@ -385,8 +397,9 @@ def scatter_launch_seconds(dev, batch, encoder, reps, flush=None):
     n_id = sum(encoder.d)
     nr = torch.randint(0, 28, (N, 1), device=dev, dtype=torch.int32)
     Tn = torch.randn((28, 2 * dh), device=dev)
-    er0 = torch.randint(0, n_id + 4, (E, len(encoder.d) + 1), device=dev, dtype=torch.int32)
-    Te0 = torch.randn((n_id + 4, dh), device=dev)
+    from gsn_b200.fused import MERGE_MAX_ROWS, _merge_edge_columns
+    Te0, eg = _merge_edge_columns(torch.randn((n_id + 4, dh), device=dev), _edge_cols(encoder), MERGE_MAX_ROWS)
+    er0 = torch.randint(0, Te0.shape[0], (E, eg['n_groups']), device=dev, dtype=torch.int32)
 
     def later():
         ops.general_edge_idx(plan, dh, P=P, edge_rows=er1, Te=Te1, edge_rows_csr=True)

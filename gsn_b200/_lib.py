@@ -48,6 +48,7 @@ _SIGNATURES = {
     'gsn_tc_force_presplit': (ctypes.c_int, [ctypes.c_int]),
     'gsn_pool_ptr': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     'gsn_encode_rows': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _vp]),
+    'gsn_encode_rows_grouped': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     'gsn_dgn_aggregate_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32,
                                              ctypes.c_float, _vp, _vp]),
 }

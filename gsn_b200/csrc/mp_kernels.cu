@@ -563,124 +563,6 @@ tab_tight_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
     S4[t] = acc;
 }
 
-// Variant of the lean kernel that keeps the L1 data pipe free for the row gathers (ncu: the lean kernel sits at 88 %
-// of l1tex data-pipe wavefronts, not at DRAM): the BatchNorm affine is either folded upstream (AFFINE = false) or kept
-// in registers, and a table of <= 4 categorical rows (the bond types) lives in registers instead of being re-read.
-template <bool TE_REGS, bool AFFINE>
-__global__ void __launch_bounds__(kMpThreads, 6) general_edge_p1b_kernel(const __grid_constant__ GenIdxParams p, int te_rows) {
-    const int dh = p.dh;
-    const int cpr = dh / 4;
-    int64_t t = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
-    if (t >= p.N * cpr) return;
-    const int64_t row = t / cpr;
-    const int c = (int)(t % cpr) * 4;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 pi = __ldg(reinterpret_cast<const float4 *>(p.P + row * (2 * dh) + c));
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = z;
-    if (AFFINE) {
-        if (p.scale) sc = __ldg(reinterpret_cast<const float4 *>(p.scale + c));
-        if (p.shift) sf = __ldg(reinterpret_cast<const float4 *>(p.shift + c));
-        // (pi + pj + te) * sc + sf  ==  fma(pj + te, sc, fma(pi, sc, sf)) up to rounding; keep the reference order instead
-    }
-    float4 t0 = z, t1 = z, t2 = z, t3 = z;
-    if (TE_REGS) {
-        const float4 *T = reinterpret_cast<const float4 *>(p.Te + c);
-        t0 = __ldg(T);
-        if (te_rows > 1) t1 = __ldg(T + (dh / 4));
-        if (te_rows > 2) t2 = __ldg(T + 2 * (dh / 4));
-        if (te_rows > 3) t3 = __ldg(T + 3 * (dh / 4));
-    }
-    float4 acc = z;
-    const float *Pj = p.P + dh + c;
-    const float *Te = p.Te + c;
-    const int kend = p.rowptr[row + 1];
-    for (int k = p.rowptr[row]; k < kend; ++k) {
-        const int j = __ldg(p.nbr + k);
-        const int r = __ldg(p.edge_rows + k);
-        const float4 pj = __ldg(reinterpret_cast<const float4 *>(Pj + (int64_t)j * (2 * dh)));
-        float4 te;
-        if (TE_REGS) te = r == 0 ? t0 : (r == 1 ? t1 : (r == 2 ? t2 : t3));
-        else te = __ldg(reinterpret_cast<const float4 *>(Te + (int64_t)r * dh));
-        float4 h = make_float4(pi.x + pj.x + te.x, pi.y + pj.y + te.y, pi.z + pj.z + te.z, pi.w + pj.w + te.w);
-        if (AFFINE) { h.x = fmaf(h.x, sc.x, sf.x); h.y = fmaf(h.y, sc.y, sf.y); h.z = fmaf(h.z, sc.z, sf.z); h.w = fmaf(h.w, sc.w, sf.w); }
-        acc.x += apply_act(h.x, p.act); acc.y += apply_act(h.y, p.act);
-        acc.z += apply_act(h.z, p.act); acc.w += apply_act(h.w, p.act);
-    }
-    *reinterpret_cast<float4 *>(p.S + row * dh + c) = acc;
-}
-
-// Warp-cooperative form of the same layer: one warp owns G consecutive rows (all dh channels, 4 per lane per
-// 128-column pass).  The index chain rowptr -> nbr -> P_j that every thread of the lean kernel walks on its own is
-// walked ONCE per warp: lanes 0..G fetch the row pointers, the warp fetches up to 32 neighbour ids / bond rows with
-// one coalesced load each, and the values are handed round with shfl.  The gathers of U edges plus the G own rows
-// are all issued before the first is consumed, so each lane keeps (U + G) x 16 B in flight instead of 16 B.
-template <int G, int U>
-__global__ void __launch_bounds__(kMpThreads) general_edge_p1_warp_kernel(const __grid_constant__ GenIdxParams p) {
-    const int dh = p.dh;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * kMpThreads + threadIdx.x) >> 5;
-    const int64_t r0 = warp * G;
-    if (r0 >= p.N) return;
-    const int nrows = (int)min((int64_t)G, p.N - r0);
-    const int rp = __ldg(p.rowptr + r0 + min(lane, nrows));
-    const int kb = __shfl_sync(0xffffffffu, rp, 0), ke = __shfl_sync(0xffffffffu, rp, nrows);
-    for (int cb = 0; cb < dh; cb += 128) {
-        const int c = cb + lane * 4;
-        const bool on = c < dh;
-        float4 pi[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-            pi[g] = (on && g < nrows) ? __ldg(reinterpret_cast<const float4 *>(p.P + (r0 + g) * (2 * dh) + c))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on && p.scale) sc = __ldg(reinterpret_cast<const float4 *>(p.scale + c));
-        if (on && p.shift) sf = __ldg(reinterpret_cast<const float4 *>(p.shift + c));
-        const float *Pj = p.P + dh + (on ? c : 0);
-        const float *Te = p.Te + (on ? c : 0);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 pic = pi[0];
-        int cur = 0;
-        int nxt = __shfl_sync(0xffffffffu, rp, 1);
-        for (int base = kb; base < ke; base += 32) {
-            const int n = min(32, ke - base);
-            int jl = 0, tl = 0;
-            if (lane < n) { jl = __ldg(p.nbr + base + lane); tl = __ldg(p.edge_rows + base + lane); }
-            for (int u0 = 0; u0 < n; u0 += U) {
-                float4 pj[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = __shfl_sync(0xffffffffu, jl, (u0 + u) & 31);
-                    if (u0 + u < n) pj[u] = __ldg(reinterpret_cast<const float4 *>(Pj + (int64_t)j * (2 * dh)));
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int t = __shfl_sync(0xffffffffu, tl, (u0 + u) & 31);
-                    if (u0 + u < n) {
-                        const float4 te = __ldg(reinterpret_cast<const float4 *>(Te + (int64_t)t * dh));   // L1-resident table row
-                        const int k = base + u0 + u;
-                        while (k >= nxt) {                    // warp-uniform: rows are contiguous in k
-                            if (on) *reinterpret_cast<float4 *>(p.S + (r0 + cur) * dh + c) = acc;
-                            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                            ++cur;
-                            nxt = __shfl_sync(0xffffffffu, rp, cur + 1);
-#pragma unroll
-                            for (int g = 1; g < G; ++g) if (g == cur) pic = pi[g];
-                        }
-                        acc.x += apply_act(fmaf(pic.x + pj[u].x + te.x, sc.x, sf.x), p.act);
-                        acc.y += apply_act(fmaf(pic.y + pj[u].y + te.y, sc.y, sf.y), p.act);
-                        acc.z += apply_act(fmaf(pic.z + pj[u].z + te.z, sc.z, sf.z), p.act);
-                        acc.w += apply_act(fmaf(pic.w + pj[u].w + te.w, sc.w, sf.w), p.act);
-                    }
-                }
-            }
-        }
-        for (; cur < nrows; ++cur) {
-            if (on) *reinterpret_cast<float4 *>(p.S + (r0 + cur) * dh + c) = acc;
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-}
-
 // Lean specialisation for the fully categorical layer (layer 0 of the ZINC / IMDB recipes): no dense operand at
 // all, one node column (atom type) and C edge columns (identifier ranks, bond type), edge rows in CSR order.
 // 32 registers (full occupancy): every term is an L1/L2-resident table row reached through a dependent index load.
@@ -895,6 +777,66 @@ extern "C" int gsn_mp_general_edge_fwd(const int32_t *d_rowptr, const int32_t *d
     return GSN_OK;
 }
 
+// Grouped form: the columns of one group form a mixed-radix number (digit = rank, weight = mult), so a group of
+// categorical columns with a small joint vocabulary addresses ONE row of a pre-summed table instead of one row per
+// column (layer 0 of the ZINC recipe: 7 edge columns -> 3 lookups per edge in the message kernel).
+struct EncodeGroupedParams {
+    EncodeParams e;
+    int group[GSN_MAX_ENCODE_COLS], mult[GSN_MAX_ENCODE_COLS], n_groups;
+};
+
+__global__ void encode_rows_grouped_kernel(const __grid_constant__ EncodeGroupedParams q) {
+    const EncodeParams &p = q.e;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.R * q.n_groups) return;
+    const int64_t r = t / q.n_groups;
+    const int g = (int)(t % q.n_groups);
+    const int64_t rs = p.perm ? (int64_t)__ldg(p.perm + r) : r;
+    int acc = 0;
+    for (int c = 0; c < p.n_cols; ++c) {
+        if (q.group[c] != g) continue;
+        const GsnEncodeCol &col = p.col[c];
+        const int64_t v = __ldg(col.src + rs * col.stride);
+        int rank;
+        if (col.vocab_end > col.vocab_begin) {
+            int lo = col.vocab_begin, hi = col.vocab_end;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (__ldg(p.vocab + mid) < v) lo = mid + 1; else hi = mid;
+            }
+            rank = lo - col.vocab_begin;
+            const int last = col.vocab_end - col.vocab_begin - 1;
+            if (rank > last) rank = last;
+        } else {
+            rank = (int)v;
+        }
+        acc += col.table_off + rank * q.mult[c];
+    }
+    p.out[t] = acc;
+}
+
+extern "C" int gsn_encode_rows_grouped(const GsnEncodeCol *h_cols, int32_t n_cols, const int32_t *h_group,
+                                       const int32_t *h_mult, int32_t n_groups, const int64_t *d_vocab,
+                                       const int32_t *d_perm, int64_t R, int32_t *d_out, void *stream_) {
+    if (!h_cols || !h_group || !h_mult || n_cols < 1 || n_cols > GSN_MAX_ENCODE_COLS || n_groups < 1 || n_groups > n_cols ||
+        R < 0 || !d_out)
+        return GSN_E_INVALID;
+    if (R == 0) return GSN_OK;
+    EncodeGroupedParams q;
+    for (int i = 0; i < n_cols; ++i) {
+        if (!h_cols[i].src || h_group[i] < 0 || h_group[i] >= n_groups || h_mult[i] < 1) return GSN_E_INVALID;
+        if (h_cols[i].vocab_end > h_cols[i].vocab_begin && !d_vocab) return GSN_E_INVALID;
+        q.e.col[i] = h_cols[i];
+        q.group[i] = h_group[i];
+        q.mult[i] = h_mult[i];
+    }
+    q.e.n_cols = n_cols; q.e.vocab = d_vocab; q.e.perm = d_perm; q.e.R = R; q.e.out = d_out; q.n_groups = n_groups;
+    encode_rows_grouped_kernel<<<(unsigned)ceil_div(R * n_groups, 256), 256, 0, (cudaStream_t)stream_>>>(q);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_encode_rows_grouped");
+    return GSN_OK;
+}
+
 extern "C" int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d_vocab, const int32_t *d_perm,
                                int64_t R, int32_t *d_out, void *stream_) {
     if (!h_cols || n_cols < 1 || n_cols > GSN_MAX_ENCODE_COLS || R < 0 || !d_out) return GSN_E_INVALID;
@@ -926,6 +868,7 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool v4 = dh % 4 == 0 && aligned16(d_P) && aligned16(d_Q) && aligned16(d_S) && aligned16(d_Tn) && aligned16(d_Te);
     (void)te_rows;
+    static const bool no_tight = getenv("GSN_NO_TIGHT") != nullptr;      // A/B aid (scripts/p1_variants.py)
     const int cpr4 = dh / 4;
     const bool pow2 = v4 && (cpr4 & (cpr4 - 1)) == 0;
     int sh = 0;
@@ -933,7 +876,7 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
     // 32-bit element indexing: float4 offsets into P / Tn ([rows, 2dh]), S and the CSR-ordered edge rows
     const bool tight = pow2 && !d_scale && !d_shift && edge_rows_csr && N * 2 * cpr4 < (int64_t)1 << 31 &&
                        E * (int64_t)(n_edge_cols > 0 ? n_edge_cols : 1) < (int64_t)1 << 31 &&
-                       (int64_t)te_rows * cpr4 < (int64_t)1 << 31 && !getenv("GSN_NO_TIGHT");
+                       (int64_t)te_rows * cpr4 < (int64_t)1 << 31 && !no_tight;
     if (tight && !d_Q && ((d_P && n_node_cols == 0 && n_edge_cols == 1) || (!d_P && n_node_cols == 1 && n_edge_cols >= 1))) {
         const uint32_t total = (uint32_t)(N * cpr4);
         const unsigned grid = (unsigned)ceil_div(total, kMpThreads);
@@ -961,31 +904,6 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
         return GSN_OK;
     }
     if (v4 && d_P && !d_Q && n_node_cols == 0 && n_edge_cols == 1 && edge_rows_csr) {
-        static const int variant = getenv("GSN_P1_VARIANT") ? atoi(getenv("GSN_P1_VARIANT")) : 0;
-        if (variant >= 6) {
-            const unsigned grid = (unsigned)ceil_div(N * (dh / 4), kMpThreads);
-            const bool aff = d_scale || d_shift;
-            const bool regs = te_rows >= 1 && te_rows <= 4 && variant != 6;
-            if (regs && aff) general_edge_p1b_kernel<true, true><<<grid, kMpThreads, 0, stream>>>(p, te_rows);
-            else if (regs) general_edge_p1b_kernel<true, false><<<grid, kMpThreads, 0, stream>>>(p, te_rows);
-            else if (aff) general_edge_p1b_kernel<false, true><<<grid, kMpThreads, 0, stream>>>(p, te_rows);
-            else general_edge_p1b_kernel<false, false><<<grid, kMpThreads, 0, stream>>>(p, te_rows);
-            GSN_BUMP(1);
-            GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");
-            return GSN_OK;
-        }
-        if (variant > 0) {
-            const int G = variant == 1 ? 4 : variant == 2 ? 4 : variant == 3 ? 8 : variant == 4 ? 2 : 8;
-            const unsigned grid = (unsigned)ceil_div(ceil_div(N, G) * 32, kMpThreads);
-            if (variant == 1) general_edge_p1_warp_kernel<4, 4><<<grid, kMpThreads, 0, stream>>>(p);
-            else if (variant == 2) general_edge_p1_warp_kernel<4, 8><<<grid, kMpThreads, 0, stream>>>(p);
-            else if (variant == 3) general_edge_p1_warp_kernel<8, 8><<<grid, kMpThreads, 0, stream>>>(p);
-            else if (variant == 4) general_edge_p1_warp_kernel<2, 4><<<grid, kMpThreads, 0, stream>>>(p);
-            else general_edge_p1_warp_kernel<8, 4><<<grid, kMpThreads, 0, stream>>>(p);
-            GSN_BUMP(1);
-            GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");
-            return GSN_OK;
-        }
         general_edge_p1_kernel<4><<<(unsigned)ceil_div(N * (dh / 4), kMpThreads), kMpThreads, 0, stream>>>(p);
         GSN_BUMP(1);
         GSN_LAUNCH_OK("gsn_mp_general_edge_idx_fwd");

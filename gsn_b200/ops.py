@@ -324,6 +324,26 @@ def encode_rows(columns, vocab, num_rows, device, perm=None):
     return out
 
 
+def encode_rows_grouped(columns, groups, mults, n_groups, vocab, num_rows, device, perm=None):
+    """encode_rows with the columns of a group folded into one mixed-radix row index (gsn_encode_rows_grouped):
+    out[r, g] = sum_{c in group g} (table_off_c + rank_c * mult_c)"""
+    cols = (GsnEncodeCol * len(columns))()
+    for i, (src, vr, off) in enumerate(columns):
+        if src.dtype != torch.int64:
+            raise ValueError('categorical columns must be int64')
+        cols[i].src, cols[i].stride = src.data_ptr(), (src.stride(0) if src.dim() else 1)
+        cols[i].vocab_begin, cols[i].vocab_end = (0, 0) if vr is None else (int(vr[0]), int(vr[1]))
+        cols[i].table_off = int(off)
+    gr = (ctypes.c_int32 * len(columns))(*[int(g) for g in groups])
+    mu = (ctypes.c_int32 * len(columns))(*[int(m) for m in mults])
+    out = torch.empty((num_rows, n_groups), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.call('encode_rows', 'gsn_encode_rows_grouped', ctypes.cast(cols, ctypes.c_void_p), len(columns),
+                  ctypes.cast(gr, ctypes.c_void_p), ctypes.cast(mu, ctypes.c_void_p), n_groups, _lib.ptr(vocab),
+                  _lib.ptr(perm), num_rows, _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
 def general_edge_idx(plan, dh, P=None, Q=None, node_rows=None, Tn=None, edge_rows=None, Te=None, scale=None, shift=None,
                      activation='relu', edge_rows_csr=False):
     """S[i] = sum_e act((P_i + P_j + sum Tn[node rows] + Q_e + sum Te[edge rows]) * scale + shift)"""

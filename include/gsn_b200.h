@@ -285,6 +285,14 @@ typedef struct GsnEncodeCol {
 int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d_vocab, const int32_t *d_perm, int64_t R,
                     int32_t *d_out, void *stream);   /* d_perm (optional): out row r encodes source row d_perm[r] */
 
+/* Grouped form: columns with the same h_group[c] are folded into ONE output column as a mixed-radix number,
+ *   out[r, g] = sum_{c in g} (table_off_c + rank_c * h_mult[c]),
+ * which addresses a pre-summed table of the group's joint vocabulary (gsn_b200/fused.py builds it): the message
+ * kernel then gathers one table row per group instead of one per column. */
+int gsn_encode_rows_grouped(const GsnEncodeCol *h_cols, int32_t n_cols, const int32_t *h_group, const int32_t *h_mult,
+                            int32_t n_groups, const int64_t *d_vocab, const int32_t *d_perm, int64_t R, int32_t *d_out,
+                            void *stream);
+
 /*
  * 'general' message kind with categorical inputs kept as indices (layer 0 of the ZINC /
  * IMDB recipes: x, edge features and identifiers are one-hot, so the first Linear of msg_fn

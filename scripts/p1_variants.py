@@ -1,5 +1,6 @@
-"""A/B of the layer>=1 message kernel variants (GSN_P1_VARIANT) at a given batch: time + checksum.
-python scripts/p1_variants.py --batch 131072"""
+"""A/B of the tight message kernels against the lean ones they replaced (suffix x = GSN_NO_TIGHT, n = no scale/shift
+operands, as fused.py calls them) at a given batch: time + checksum of the output bits.
+python scripts/p1_variants.py --batch 131072 --variants 0nx,0n"""
 import argparse, os, subprocess, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 sys.path.insert(0, ROOT)
@@ -46,7 +47,7 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=131072)
     ap.add_argument('--child', action='store_true')
-    ap.add_argument('--variants', default='0,1,2,3,4,5')
+    ap.add_argument('--variants', default='0nx,0n')
     a = ap.parse_args()
     if a.child:
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

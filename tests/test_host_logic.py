@@ -54,3 +54,32 @@ def test_collate_matches_pyg_semantics():
     for i, g in enumerate(graphs):
         e0, e1 = int(b.edge_ptr[i]), int(b.edge_ptr[i + 1])
         assert torch.equal(b.edge_index[:, e0:e1], g.edge_index + int(b.node_ptr[i]))
+
+
+def test_merge_edge_columns_mixed_radix_tables():
+    """fused.py: groups of categorical edge columns -> one pre-summed table per group; the mixed-radix row index of a
+    tuple of ranks must address the sum of the per-column rows"""
+    import itertools
+    import torch
+    from gsn_b200.fused import _merge_edge_columns
+    dims = [2, 3, 5, 7, 8, 10, 4]
+    cols, o = [], 0
+    for d in dims:
+        cols.append((d, o))
+        o += d
+    Te = torch.randn((o, 8), generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    tab, eg = _merge_edge_columns(Te, cols, 64)
+    assert eg['n_groups'] == 3 and eg['group'] == [0, 0, 0, 1, 1, 2, 2]          # 2*3*5=30 | 7*8=56 | 10*4=40
+    assert tab.shape[0] == 30 + 56 + 40
+    g = torch.Generator().manual_seed(1)
+    for _ in range(50):
+        ranks = [int(torch.randint(0, d, (1,), generator=g)) for d in dims]
+        rows = [0] * eg['n_groups']
+        for c, r in enumerate(ranks):
+            rows[eg['group'][c]] += eg['off'][c] + r * eg['mult'][c]
+        got = sum(tab[r] for r in rows)
+        exp = sum(Te[cols[c][1] + r] for c, r in enumerate(ranks))
+        torch.testing.assert_close(got, exp, atol=1e-12, rtol=0)
+    # a column larger than the cap stands alone; single column -> identity table
+    tab1, eg1 = _merge_edge_columns(Te[:100 if o >= 100 else o], [(o, 0)], 16)
+    assert eg1['n_groups'] == 1 and eg1['mult'] == [1] and torch.equal(tab1, Te)
