@@ -139,6 +139,32 @@ def to_tensors(b, pad_to=None, pin=False, device=None):
     return t
 
 
+def batch_variants(b, n, seed):
+    """n distinct batches with the SAME shapes as b (CUDA graphs need static shapes): the graphs of b in a different
+    order (so edge_index, node_ptr, batch differ) with fresh random atom / bond types.  Stacked along a leading axis."""
+    rng = np.random.default_rng(seed)
+    node_ptr, edge_ptr, ei = b['node_ptr'], b['edge_ptr'], b['edge_index']
+    G = len(node_ptr) - 1
+    sizes, esizes = np.diff(node_ptr), np.diff(edge_ptr)
+    g_of_e = np.repeat(np.arange(G), esizes)
+    local = ei - node_ptr[g_of_e][None, :]
+    N, E = int(node_ptr[-1]), int(edge_ptr[-1])
+    out = {k: [] for k in ('edge_index', 'node_ptr', 'x', 'edge_features', 'batch', 'degrees')}
+    for _ in range(n):
+        perm = rng.permutation(G)                          # new position p holds old graph perm[p]
+        nptr = np.concatenate([[0], np.cumsum(sizes[perm])]).astype(np.int64)
+        e_order = np.concatenate([np.arange(edge_ptr[g], edge_ptr[g + 1]) for g in perm])
+        pos_of_e = np.repeat(np.arange(G), esizes[perm])
+        new_ei = local[:, e_order] + nptr[pos_of_e][None, :]
+        out['edge_index'].append(new_ei)
+        out['node_ptr'].append(nptr)
+        out['x'].append(rng.integers(0, 28, size=(N, 1), dtype=np.int64))
+        out['edge_features'].append(rng.integers(1, 4, size=(E, 1), dtype=np.int64))
+        out['batch'].append(np.repeat(np.arange(G, dtype=np.int64), sizes[perm]))
+        out['degrees'].append(np.bincount(new_ei[0], minlength=N).astype(np.float32))
+    return {k: torch.from_numpy(np.stack(v)) for k, v in out.items()}
+
+
 # ======================================================================================
 # our arm
 # ======================================================================================
@@ -212,32 +238,112 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         return sum(a.elapsed_time(b) for a, b in evs)      # ms
 
-    # ---- value: device-resident inputs, CUDA-graph replay
+    # ---- single stream, one step at a time, L2 flushed before every step (the latency of ONE step)
     for _ in range(args.warmup):
         pipe.replay()
     with Clocks(local_rank) as clk:
-        ms_total = timed_steps(lambda: pipe.replay(), args.steps)
-        # ---- e2e: pinned host inputs -> H2D -> step -> D2H
-        out_host = torch.empty((G, 1), dtype=torch.float32).pin_memory()
+        ms_single = timed_steps(lambda: pipe.replay(), args.steps) / args.steps
 
-        def e2e_step():
-            pipe.load(host_in)
-            o = pipe.replay()
-            out_host.copy_(o, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        for _ in range(args.warmup):
-            e2e_step()
-        ms_e2e = timed_steps(e2e_step, args.steps)
-    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    d2h = out_host.numel() * out_host.element_size()
+        # ---- value: whole-job throughput.  At B=128 one step is a chain of ~26 dependent launches that each fill a
+        # fraction of the 148 SMs, so S steps on DIFFERENT batches are kept in flight (S captured graphs on S streams),
+        # as a server overlapping consecutive batches would.  Every step copies ITS OWN batch out of a pool of
+        # `--pool` distinct batches (same shapes, other graph order / features; > L2 in total, no batch is used twice
+        # inside a timed region that fits the pool) into the graph's input buffers, inside the timed region; L2 is
+        # flushed once before the region (steps overlap, so it cannot be flushed between them).
+        S, P = max(1, args.streams), max(args.pool, 2 * max(1, args.streams))
+        pool_host = {k: v.pin_memory() for k, v in batch_variants(b0, P, seed=4242 + rank).items()}
+        pool_dev = {k: v.to(dev) for k, v in pool_host.items()}
+        pipes = [pipe] + [GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64).capture(
+            dev_in, warmup=3) for _ in range(S - 1)]
+        streams = [torch.cuda.Stream() for _ in range(S)]
+        out_host = torch.empty((args.steps + args.warmup, G, 1), dtype=torch.float32).pin_memory()
+
+        def run_steps(k, start, src, d2h):
+            main = torch.cuda.current_stream()
+            for st in streams:
+                st.wait_stream(main)
+            for i in range(k):
+                with torch.cuda.stream(streams[i % S]):
+                    pipes[i % S].load({key: val[(start + i) % P] for key, val in src.items()})
+                    o = pipes[i % S].replay()
+                    if d2h:
+                        out_host[i].copy_(o, non_blocking=True)
+            for st in streams:
+                main.wait_stream(st)
+
+        def timed_region(src, d2h):
+            run_steps(args.warmup, 0, src, d2h)
+            barrier()
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run_steps(args.steps, args.warmup, src, d2h)
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1)
+
+        # the pooled batches go through the same captured step: check two of them against the eager step
+        for v in (1, P - 1):
+            tv = {key: val[v].clone() for key, val in pool_dev.items()}
+            with torch.no_grad():
+                exp_v = pipe.step(tv).clone()
+            pipes[-1].load(tv)
+            got_v = pipes[-1].replay().clone()
+            torch.cuda.synchronize()
+            assert torch.allclose(got_v, exp_v, atol=1e-5, rtol=1e-5), 'pooled batch: captured step differs from eager step'
+        ms_total = timed_region(pool_dev, False)
+        # ---- e2e: every step's inputs come from PINNED HOST memory (H2D inside the region) and its predictions are
+        # read back to the host (D2H inside the region); same S streams
+        ms_e2e = timed_region(pool_host, True)
+        assert bool(torch.isfinite(out_host[:args.steps]).all())
+    h2d = sum(v[0].numel() * v[0].element_size() for v in pool_host.values())
+    d2h = out_host[0].numel() * out_host.element_size()
 
     if dist_on:
-        tt = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        tt = torch.tensor([ms_total, ms_e2e, ms_single], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-        ms_total, ms_e2e = float(tt[0]), float(tt[1])
+        ms_total, ms_e2e, ms_single = float(tt[0]), float(tt[1]), float(tt[2])
     ms_per_step = ms_total / args.steps
     value = world * G / (ms_per_step * 1e-3)
     e2e_value = world * G / (ms_e2e / args.steps * 1e-3)
+
+    # ---- informative only: other stream counts on ONE repeated batch (no pool), to show where the overlap saturates
+    concurrent = None
+    if rank == 0 and not args.no_sweep:
+        try:
+            concurrent = []
+            for S in (2, 4, 12):
+                pipes = [pipe] + [GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64).capture(
+                    dev_in, warmup=3) for _ in range(S - 1)]
+                streams = [torch.cuda.Stream() for _ in range(S)]
+                K = max(args.steps, 40)
+                for p_ in pipes:
+                    p_.load(dev_in)
+
+                def run(k):
+                    main = torch.cuda.current_stream()
+                    for st in streams:
+                        st.wait_stream(main)
+                    for i in range(k):
+                        with torch.cuda.stream(streams[i % S]):
+                            pipes[i % S].replay()
+                    for st in streams:
+                        main.wait_stream(st)
+                run(2 * S)
+                torch.cuda.synchronize()
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run(K)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                ok = all(torch.allclose(p_._out, ref_out, atol=1e-5, rtol=1e-5) for p_ in pipes)
+                concurrent.append({'streams': S, 'steps': K, 'graphs_per_s': K * G / (ms * 1e-3), 'ms_per_step': ms / K,
+                                   'outputs_match': bool(ok)})
+                del pipes
+        except Exception as ex:
+            concurrent = [{'error': repr(ex)[:200]}]
 
     line = None
     if rank == 0:
@@ -351,6 +457,15 @@ def run_ours(args, rank, world, local_rank):
             except Exception as ex:
                 roof_large = {'error': repr(ex)[:200]}
         cpu = cpu_baseline(pool[0], sds_oracle(), encoder, model, budget_s=12.0)
+        eager = None
+        if not args.no_sweep:
+            try:
+                ids_dev = counting.count_batch(dev_in['edge_index'], dev_in['node_ptr'], sds, False, 'local',
+                                               max_nodes_per_graph=64)
+                eager = torch_eager_gpu(pool[0], ids_dev, encoder, model, dev)
+                eager['max_abs_diff_vs_ours'] = float((eager.pop('out') - ref_out).abs().max())
+            except Exception as ex:
+                eager = {'error': repr(ex)[:200]}
         line = {
             'metric': 'graphs/sec preprocess+forward (ZINC batch)', 'value': value, 'unit': 'graphs/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
@@ -359,16 +474,24 @@ def run_ours(args, rank, world, local_rank):
             'config': {'workload': f'ZINC-shaped synthetic batch B={B} per GPU (N={N}, E={E}); COUNT cycles k<=8 edge '
                                    f'scope non-induced + one_hot_unique encode + GNNSubstructures forward '
                                    f'(GSN_edge_sparse general, id_scope local, {N_LAYERS} layers, d_out {D_OUT})',
-                       'batch_per_gpu': B, 'N': N, 'E': E, 'id_columns': encoder.d, 'l2': 'flushed between steps '
-                       '(256 MiB memset outside the timed event pairs)', 'cuda_graph': True,
+                       'batch_per_gpu': B, 'N': N, 'E': E, 'id_columns': encoder.d, 'l2': f'inputs larger than L2: every step reads its own batch from '
+                       f'a pool of {P} distinct same-shape batches ({P * h2d / 1e6:.0f} MB > 126 MB L2), none reused inside a '
+                       'timed region; one 256 MiB L2 flush before the region (the steps overlap); single_stream: L2 flushed '
+                       'before every step', 'cuda_graph': True, 'streams': S, 'pool': P,
                        'parallelism': f'batch-sharded x{world}, no data-path collective'},
             'edges_per_s': world * E / (ms_per_step * 1e-3),
+            'single_stream': {'ms_per_step': ms_single, 'graphs_per_s': world * G / (ms_single * 1e-3),
+                              'note': 'one step at a time on one stream, L2 flushed before every step, one fixed batch: the '
+                                      'LATENCY of a step; `value` keeps `streams` steps on different batches in flight'},
             'e2e': {'value': e2e_value, 'unit': 'graphs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': int(my_launches_per_step) * args.steps,
+            'gpu_launches': int(my_launches_per_step) * args.steps,     # our kernels; + 6 input copies per step
             'gpu_launches_per_step': int(my_launches_per_step),
             'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep, 'scatter_kernels': scatter_kernels,
-            'roofline_large_batch': roof_large,
+            'roofline_large_batch': roof_large, 'torch_eager_gpu': eager,
+            'concurrent_streams': {'note': 'informative: other stream counts, ONE batch replayed (no pool), one L2 flush '
+                                           'before the region',
+                                   'runs': concurrent},
         }
     return line
 
@@ -509,6 +632,37 @@ def cpu_step_fn(batch, sds_o, encoder, model, threads):
     return step
 
 
+def torch_eager_gpu(batch, ids_dev, encoder, model, dev, reps=20):
+    """the incumbent on the box -- the reference's MP forward as eager PyTorch on the same GPU
+    (oracle/mp_ref.py restates the reference layers op by op; COUNT has no PyTorch form, so this is the forward
+    only, identifiers pre-computed and pre-encoded).  Baseline leg, like cpu_baseline: never the product path."""
+    from oracle import mp_ref
+    sd = {k: v.detach().to(dev) for k, v in model.state_dict().items()}
+    args = model_args(encoder.d)
+    args['d_in_id'] = encoder.d
+    args['d_in_node_encoder'], args['d_in_edge_encoder'] = [28], [4]
+    cfgs = [dict(uses_ids=(i == 0), uses_ef=True, msg_kind='general', id_scope='local', flow='source_to_target',
+                 activation_name='relu', bn=True, degree_as_tag=False, retain_features=True,
+                 edge_embedding='one_hot_encoder', id_embedding='one_hot_encoder', extend_dims=True) for i in range(N_LAYERS)]
+    data = {k: torch.from_numpy(batch[k]).to(dev) for k in ('edge_index', 'batch', 'x', 'edge_features', 'degrees')}
+    data['identifiers'] = encoder(ids_dev)
+    with torch.no_grad():
+        for _ in range(3):
+            out = mp_ref.gnn_substructures_forward(args, sd, data, cfgs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = mp_ref.gnn_substructures_forward(args, sd, data, cfgs)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    G = len(batch['node_ptr']) - 1
+    return {'forward_ms': ms, 'forward_graphs_per_s': G / (ms * 1e-3), 'out': out,
+            'what': 'reference MP forward (one-hot encoders, [E,d] gathers + cat, E-row message MLP, index_add_) as eager PyTorch '
+                    'on the same B200, fp32 (TF32 off); forward only -- COUNT and the encoding are not included'}
+
+
 def cpu_baseline(batch, sds_o, encoder, model, budget_s):
     threads = os.cpu_count() or 1
     step = cpu_step_fn(batch, sds_o, encoder, model, threads)
@@ -572,6 +726,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=128)
     ap.add_argument('--no-sweep', action='store_true')
+    ap.add_argument('--streams', type=int, default=8, help='independent steps in flight (CUDA streams / captured graphs)')
+    ap.add_argument('--pool', type=int, default=640, help='distinct same-shape input batches cycled through (> L2 in total)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

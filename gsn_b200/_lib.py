@@ -51,6 +51,8 @@ _SIGNATURES = {
     'gsn_encode_rows_grouped': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     'gsn_dgn_aggregate_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32,
                                              ctypes.c_float, _vp, _vp]),
+    'gsn_dgn_aggregate_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32,
+                                             ctypes.c_float, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

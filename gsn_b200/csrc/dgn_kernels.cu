@@ -145,23 +145,194 @@ __global__ void __launch_bounds__(256) dgn_aggregate_kernel(const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------ backward
+// d(out)/d(h) of dgn_aggregate_kernel.  Same ownership as the forward (one thread per destination node and 4-channel
+// chunk): it recomputes the node's statistics / directional weights and writes, for every in-edge k (j -> i), the
+// gradient that flows to the SOURCE row h[j] into M[eid[k], :] (edge-id order) plus the gradient to its own row
+// (the -(sum w) h_i term of the dx aggregators) into SG[i, :].  grad_h = SG + segment-sum of M over the grouping by
+// source (gsn_mp_segment_sum with the transposed plan): deterministic, no float atomics.  Formulas = autograd of
+// aggregators.py:8-69 (relu'(0) = 0, sign(0) = 0, max / min route to the first extremum in mailbox order).
+template <int VEC>
+__global__ void __launch_bounds__(256) dgn_aggregate_bwd_kernel(const __grid_constant__ DgnParams p, const float *__restrict__ gout,
+                                                                float *__restrict__ M, float *__restrict__ SG) {
+    const int d = p.d, cpr = d / VEC;
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t i = t / cpr;
+    const int c = (int)(t % cpr) * VEC;
+    const int k0 = __ldg(p.rowptr + i), k1 = __ldg(p.rowptr + i + 1);
+    const int D = k1 - k0;
+    const int AD = p.n_aggr * d;
+    float sg[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) sg[v] = 0.f;
+    if (D == 0) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) SG[i * d + c + v] = 0.f;
+        return;
+    }
+    float sfac[GSN_DGN_MAX_SCALERS];
+    for (int s = 0; s < p.n_scalers; ++s) {
+        float f = 1.0f;
+        if (p.n_scalers > 1) {
+            const double lg = log((double)D + 1.0);
+            if (p.scaler_kind[s] == 1) f = (float)(lg / (double)p.avg_log);
+            else if (p.scaler_kind[s] == 2) f = (float)((double)p.avg_log / lg);
+        }
+        sfac[s] = f;
+    }
+    const float *grow = gout + i * (int64_t)(AD * p.n_scalers);
+    auto upstream = [&](int a, float (&G)[VEC]) {            // sum over the scaler blocks of aggregator a
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) G[v] = 0.f;
+        for (int s = 0; s < p.n_scalers; ++s) {
+            float gv[VEC];
+            ld_vec<VEC>(grow + s * AD + a * d + c, gv);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) G[v] = fmaf(sfac[s], gv[v], G[v]);
+        }
+    };
+    float hin[VEC];
+    ld_vec<VEC>(p.h + i * d + c, hin);
+    // ---- basic aggregators: upstream gradients summed per kind, one statistics pass, one emit pass
+    float Gk[6][VEC];
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) Gk[q][v] = 0.f;
+    bool any_basic = false;
+    for (int a = 0; a < p.n_aggr; ++a) {
+        const int kind = p.aggr_kind[a];
+        if (kind > GSN_DGN_VAR) continue;
+        any_basic = true;
+        float G[VEC];
+        upstream(a, G);
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+            if (q == kind)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) Gk[q][v] += G[v];
+    }
+    float s1[VEC], s2[VEC], mx[VEC], mn[VEC];
+    int kmx[VEC], kmn[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { s1[v] = 0.f; s2[v] = 0.f; mx[v] = -INFINITY; mn[v] = INFINITY; kmx[v] = k0; kmn[v] = k0; }
+    if (any_basic) {
+        for (int k = k0; k < k1; ++k) {
+            float xs[VEC];
+            ld_vec<VEC>(p.h + (int64_t)__ldg(p.nbr + k) * d + c, xs);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float x = xs[v];
+                s1[v] += x; s2[v] = __fadd_rn(s2[v], __fmul_rn(x, x));
+                if (x > mx[v]) { mx[v] = x; kmx[v] = k; }
+                if (x < mn[v]) { mn[v] = x; kmn[v] = k; }
+            }
+        }
+    }
+    float m1[VEC], cvar[VEC];          // mean, and d(loss)/d(var) incl. the std branch, zero where relu clipped
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        m1[v] = __fdiv_rn(s1[v], (float)D);
+        const float raw = __fsub_rn(__fdiv_rn(s2[v], (float)D), __fmul_rn(m1[v], m1[v]));
+        const float var = fmaxf(raw, 0.f);
+        cvar[v] = raw > 0.f ? Gk[GSN_DGN_VAR][v] + Gk[GSN_DGN_STD][v] / (2.0f * sqrtf(var + kDgnEps)) : 0.f;
+    }
+    for (int k = k0; k < k1; ++k) {                       // first write of every M row of this node
+        float xs[VEC], m[VEC];
+        ld_vec<VEC>(p.h + (int64_t)__ldg(p.nbr + k) * d + c, xs);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float acc = 0.f;
+            if (any_basic) {
+                acc = Gk[GSN_DGN_MEAN][v] / (float)D + Gk[GSN_DGN_SUM][v];
+                if (k == kmx[v]) acc += Gk[GSN_DGN_MAX][v];
+                if (k == kmn[v]) acc += Gk[GSN_DGN_MIN][v];
+                acc += cvar[v] * (2.0f * (xs[v] - m1[v]) / (float)D);
+            }
+            m[v] = acc;
+        }
+        float *mrow = M + (int64_t)__ldg(p.eid + k) * d + c;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) mrow[v] = m[v];
+    }
+    // ---- directional aggregators, one at a time
+    for (int a = 0; a < p.n_aggr; ++a) {
+        const int kind = p.aggr_kind[a], fi = p.aggr_idx[a];
+        if (kind <= GSN_DGN_VAR) continue;
+        float G[VEC];
+        upstream(a, G);
+        float n_abs = 0.f, n_pos = 0.f, n_neg = 0.f, mxs = -INFINITY;
+        for (int k = k0; k < k1; ++k) {
+            const float F = dgn_field(p, fi, i, __ldg(p.nbr + k), k);
+            n_abs += fabsf(F); n_pos += fmaxf(F, 0.f); n_neg += fmaxf(-F, 0.f);
+            mxs = fmaxf(mxs, p.aggr_alpha[a] * fabsf(F));
+        }
+        float se = 0.f;
+        if (kind == GSN_DGN_DIR_SOFTMAX)
+            for (int k = k0; k < k1; ++k)
+                se += expf(p.aggr_alpha[a] * fabsf(dgn_field(p, fi, i, __ldg(p.nbr + k), k)) - mxs);
+        auto weight = [&](float F) {
+            if (kind == GSN_DGN_DIR_AV) return fabsf(F) / (n_abs + kDgnEps);
+            if (kind == GSN_DGN_DIR_SOFTMAX) return expf(p.aggr_alpha[a] * fabsf(F) - mxs) / se;
+            if (kind == GSN_DGN_DIR_DX_BALANCED)
+                return (fmaxf(F, 0.f) / (n_pos + kDgnEps) + fmaxf(-F, 0.f) / (n_neg + kDgnEps)) / 2.0f;
+            return F / (n_abs + kDgnEps);
+        };
+        float sgn[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sgn[v] = 1.0f;
+        float wsum = 0.f;
+        const bool centred = kind >= GSN_DGN_DIR_DX;          // dx, dx-no-abs, dx-balanced subtract (sum w) h_i
+        if (centred) {
+            float u[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) u[v] = 0.f;
+            for (int k = k0; k < k1; ++k) {
+                const int j = __ldg(p.nbr + k);
+                const float w = weight(dgn_field(p, fi, i, j, k));
+                wsum += w;
+                float xs[VEC];
+                ld_vec<VEC>(p.h + (int64_t)j * d + c, xs);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) u[v] += xs[v] * w;
+            }
+            if (kind != GSN_DGN_DIR_DX_NO_ABS) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float uu = u[v] - wsum * hin[v];
+                    sgn[v] = uu > 0.f ? 1.0f : (uu < 0.f ? -1.0f : 0.f);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sg[v] -= sgn[v] * G[v] * wsum;
+        }
+        for (int k = k0; k < k1; ++k) {
+            const int j = __ldg(p.nbr + k);
+            const float w = weight(dgn_field(p, fi, i, j, k));
+            float *mrow = M + (int64_t)__ldg(p.eid + k) * d + c;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) mrow[v] += sgn[v] * G[v] * w;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) SG[i * d + c + v] = sg[v];
+}
+
 }  // namespace gsn
 
 using namespace gsn;
 
-extern "C" int gsn_dgn_aggregate_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
-                                     int64_t E, const float *d_h, int32_t d, const float *d_node_field, int32_t Fn,
-                                     const float *d_edge_field, int32_t Fe, const GsnDgnAggr *h_aggr, int32_t n_aggr,
-                                     const int32_t *h_scalers, int32_t n_scalers, float avg_log, float *d_out,
-                                     void *stream_) {
-    if (N < 0 || E < 0 || d < 1 || !d_rowptr || !d_h || !d_out || !h_aggr || n_aggr < 1 || n_aggr > GSN_DGN_MAX_AGGR ||
+static int dgn_fill(DgnParams &p, const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N, int64_t E,
+                    const float *d_h, int32_t d, const float *d_node_field, int32_t Fn, const float *d_edge_field, int32_t Fe,
+                    const GsnDgnAggr *h_aggr, int32_t n_aggr, const int32_t *h_scalers, int32_t n_scalers, float avg_log) {
+    if (N < 0 || E < 0 || d < 1 || !d_rowptr || !d_h || !h_aggr || n_aggr < 1 || n_aggr > GSN_DGN_MAX_AGGR ||
         n_scalers < 1 || n_scalers > GSN_DGN_MAX_SCALERS || !h_scalers || Fn < 0 || Fe < 0)
         return GSN_E_INVALID;
     if ((Fn > 0 && !d_node_field) || (Fe > 0 && (!d_edge_field || !d_eid)) || (E > 0 && !d_nbr)) return GSN_E_INVALID;
-    DgnParams p;
     p.rowptr = d_rowptr; p.eid = d_eid; p.nbr = d_nbr; p.N = N; p.h = d_h; p.node_field = d_node_field;
     p.edge_field = d_edge_field; p.d = d; p.Fn = Fn; p.Fe = Fe; p.n_aggr = n_aggr; p.n_scalers = n_scalers;
-    p.avg_log = avg_log; p.out = d_out;
+    p.avg_log = avg_log; p.out = nullptr;
     for (int a = 0; a < n_aggr; ++a) {
         const GsnDgnAggr &g = h_aggr[a];
         if (g.kind < GSN_DGN_MEAN || g.kind > GSN_DGN_DIR_DX_BALANCED) return GSN_E_INVALID;
@@ -172,6 +343,39 @@ extern "C" int gsn_dgn_aggregate_fwd(const int32_t *d_rowptr, const int32_t *d_e
         if (h_scalers[s] < 0 || h_scalers[s] > 2) return GSN_E_INVALID;
         p.scaler_kind[s] = h_scalers[s];
     }
+    return GSN_OK;
+}
+
+extern "C" int gsn_dgn_aggregate_bwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                                     int64_t E, const float *d_h, int32_t d, const float *d_node_field, int32_t Fn,
+                                     const float *d_edge_field, int32_t Fe, const GsnDgnAggr *h_aggr, int32_t n_aggr,
+                                     const int32_t *h_scalers, int32_t n_scalers, float avg_log, const float *d_grad_out,
+                                     float *d_M, float *d_SG, void *stream_) {
+    DgnParams p;
+    const int rc = dgn_fill(p, d_rowptr, d_eid, d_nbr, N, E, d_h, d, d_node_field, Fn, d_edge_field, Fe, h_aggr, n_aggr,
+                            h_scalers, n_scalers, avg_log);
+    if (rc) return rc;
+    if (!d_grad_out || !d_SG || (E > 0 && (!d_M || !d_eid))) return GSN_E_INVALID;
+    if (N == 0) return GSN_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (d % 4 == 0) dgn_aggregate_bwd_kernel<4><<<(unsigned)ceil_div(N * (d / 4), 256), 256, 0, stream>>>(p, d_grad_out, d_M, d_SG);
+    else dgn_aggregate_bwd_kernel<1><<<(unsigned)ceil_div(N * (int64_t)d, 256), 256, 0, stream>>>(p, d_grad_out, d_M, d_SG);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_dgn_aggregate_bwd");
+    return GSN_OK;
+}
+
+extern "C" int gsn_dgn_aggregate_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N,
+                                     int64_t E, const float *d_h, int32_t d, const float *d_node_field, int32_t Fn,
+                                     const float *d_edge_field, int32_t Fe, const GsnDgnAggr *h_aggr, int32_t n_aggr,
+                                     const int32_t *h_scalers, int32_t n_scalers, float avg_log, float *d_out,
+                                     void *stream_) {
+    DgnParams p;
+    const int rc = dgn_fill(p, d_rowptr, d_eid, d_nbr, N, E, d_h, d, d_node_field, Fn, d_edge_field, Fe, h_aggr, n_aggr,
+                            h_scalers, n_scalers, avg_log);
+    if (rc) return rc;
+    if (!d_out) return GSN_E_INVALID;
+    p.out = d_out;
     if (N == 0) return GSN_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (d % 4 == 0) dgn_aggregate_kernel<4><<<(unsigned)ceil_div(N * (d / 4), 256), 256, 0, stream>>>(p);

@@ -11,8 +11,8 @@ directional_gsn/ pieces that sit either side of the counting kernel.
     DirectionalBatch (edge_index + fields + node_ptr).  type_net 'complex' / 'towers' name classes
     the reference never defines (dgn_layer.py:98-108 would raise NameError) and are not built.
 
-Forward only: the aggregation has no backward kernel yet (training DGN is out of this round's
-scope); calling backward through it raises.
+The aggregation is differentiable w.r.t. h (gsn_dgn_aggregate_bwd + the deterministic segment-sum), so
+DGNLayerSimple trains; the 'eig' fields are data (counts) and get no gradient.
 """
 from __future__ import annotations
 
@@ -60,6 +60,15 @@ def parse_aggregators(names: str):
     return out
 
 
+def _aggr_array(aggr, Fn, Fe):
+    arr = (GsnDgnAggr * len(aggr))()
+    for i, (k, f, al) in enumerate(aggr):
+        arr[i].kind, arr[i].field, arr[i].alpha = k, f, al
+        if k >= KIND['dir-av'] and f >= Fn + Fe:
+            raise IndexError(f'eig_idx {f} out of range for a vector field with {Fn + Fe} components')
+    return arr
+
+
 class _DgnAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, plan, node_field, edge_field, aggr, scalers, avg_log):
@@ -68,13 +77,9 @@ class _DgnAggregate(torch.autograd.Function):
         N, d = h.shape
         Fn = 0 if node_field is None else node_field.shape[1]
         Fe = 0 if edge_field is None else edge_field.shape[1]
-        nf = None if node_field is None else node_field.float().contiguous()
-        ef = None if edge_field is None else edge_field.float().contiguous()
-        arr = (GsnDgnAggr * len(aggr))()
-        for i, (k, f, al) in enumerate(aggr):
-            arr[i].kind, arr[i].field, arr[i].alpha = k, f, al
-            if k >= KIND['dir-av'] and f >= Fn + Fe:
-                raise IndexError(f'eig_idx {f} out of range for a vector field with {Fn + Fe} components')
+        nf = None if node_field is None else node_field.detach().float().contiguous()
+        ef = None if edge_field is None else edge_field.detach().float().contiguous()
+        arr = _aggr_array(aggr, Fn, Fe)
         sc = (ctypes.c_int32 * len(scalers))(*scalers)
         out = torch.empty((N, len(aggr) * len(scalers) * d), dtype=torch.float32, device=h.device)
         with torch.cuda.device(h.device):
@@ -82,11 +87,32 @@ class _DgnAggregate(torch.autograd.Function):
                       N, plan.E, _lib.ptr(h), d, _lib.ptr(nf), Fn, _lib.ptr(ef), Fe, ctypes.cast(arr, ctypes.c_void_p),
                       len(aggr), ctypes.cast(sc, ctypes.c_void_p), len(scalers), ctypes.c_float(avg_log), _lib.ptr(out),
                       _lib.stream_ptr())
+        ctx.save_for_backward(h)
+        ctx.rest = (plan, nf, ef, list(aggr), list(scalers), avg_log)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        raise NotImplementedError('gsn_b200.directional: the DGN aggregation is forward-only (no backward kernel yet)')
+        (h,) = ctx.saved_tensors
+        plan, nf, ef, aggr, scalers, avg_log = ctx.rest
+        N, d = h.shape
+        Fn = 0 if nf is None else nf.shape[1]
+        Fe = 0 if ef is None else ef.shape[1]
+        g = g.float().contiguous()
+        arr = _aggr_array(aggr, Fn, Fe)
+        sc = (ctypes.c_int32 * len(scalers))(*scalers)
+        M = torch.empty((max(plan.E, 1), d), dtype=torch.float32, device=h.device)
+        SG = torch.empty((N, d), dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            _lib.call('dgn_aggregate_bwd', 'gsn_dgn_aggregate_bwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid),
+                      _lib.ptr(plan.nbr), N, plan.E, _lib.ptr(h), d, _lib.ptr(nf), Fn, _lib.ptr(ef), Fe,
+                      ctypes.cast(arr, ctypes.c_void_p), len(aggr), ctypes.cast(sc, ctypes.c_void_p), len(scalers),
+                      ctypes.c_float(avg_log), _lib.ptr(g), _lib.ptr(M), _lib.ptr(SG), _lib.stream_ptr())
+        if plan.E == 0:
+            return SG, None, None, None, None, None, None
+        # messages were gathered at edge_index[0]: their gradients are summed per source row, in edge-id order
+        src_plan = ops.edge_plan(plan.edge_index, N, 'target_to_source' if plan.select == 1 else 'source_to_target')
+        return SG + ops.segment_sum(src_plan, M[:plan.E]), None, None, None, None, None, None
 
 
 def dgn_aggregate(plan, h, node_field=None, edge_field=None, aggregators='mean', scalers='identity', avg_d=None):

@@ -349,6 +349,13 @@ int gsn_dgn_aggregate_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const i
                           const float *d_h, int32_t d, const float *d_node_field, int32_t Fn, const float *d_edge_field,
                           int32_t Fe, const GsnDgnAggr *h_aggr, int32_t n_aggr, const int32_t *h_scalers,
                           int32_t n_scalers, float avg_log, float *d_out, void *stream);
+/* Backward w.r.t. h (autograd of aggregators.py:8-69; the fields are data).  Per in-edge k (j -> i) the gradient that
+ * flows to h[j] is written to d_M[eid[k], 0:d] (edge-id order, [E, d]) and the gradient to the node's own row (dx kinds)
+ * to d_SG [N, d]:  grad_h = d_SG + gsn_mp_segment_sum(plan grouped by edge_index[0], d_M).  Deterministic. */
+int gsn_dgn_aggregate_bwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N, int64_t E,
+                          const float *d_h, int32_t d, const float *d_node_field, int32_t Fn, const float *d_edge_field,
+                          int32_t Fe, const GsnDgnAggr *h_aggr, int32_t n_aggr, const int32_t *h_scalers,
+                          int32_t n_scalers, float avg_log, const float *d_grad_out, float *d_M, float *d_SG, void *stream);
 
 /* ------------------------------------------------------------------ */
 /* misc                                                                */

@@ -58,7 +58,15 @@ def main():
             fg.update_all(layer.message_func, layer.reduce_func)
             agg = fg.ndata['h'].clone()
             y = layer(graph(), h, None, snorm)
-        out[name] = dict(aggregators=aggr, scalers=scal, d_in=d_in, d_out=d_out, residual=residual, graph_norm=graph_norm,
+        # gradient of the mailbox reduction w.r.t. h through the reference's own aggregator code (autograd)
+        hr = h.clone().requires_grad_(True)
+        fg = graph()
+        fg.ndata['h'] = hr
+        fg.apply_edges(layer.pretrans_edges)
+        fg.update_all(layer.message_func, layer.reduce_func)
+        cot = torch.randn(agg.shape, generator=g)
+        (fg.ndata['h'] * cot).sum().backward()
+        out[name] = dict(cot=cot, h_grad=hr.grad.clone(), aggregators=aggr, scalers=scal, d_in=d_in, d_out=d_out, residual=residual, graph_norm=graph_norm,
                          avg_d=avg_d, edge_index=ei, batch=batch, num_nodes=N, h=h, node_field=nf, edge_field=ef,
                          snorm_n=snorm, agg=agg, state_dict={k: v.clone() for k, v in layer.state_dict().items()}, out=y)
         deg0 = int((torch.bincount(ei[1], minlength=N) == 0).sum())
