@@ -165,6 +165,28 @@ def batch_variants(b, n, seed):
     return {k: torch.from_numpy(np.stack(v)) for k, v in out.items()}
 
 
+class Packing:
+    """byte layout of one batch inside a single buffer (16-byte aligned fields): a step's inputs move with ONE copy"""
+
+    def __init__(self, example):
+        self.fields, off = [], 0
+        for k, v in example.items():
+            nbytes = v.numel() * v.element_size()
+            self.fields.append((k, off, nbytes, v.dtype, tuple(v.shape)))
+            off += (nbytes + 15) // 16 * 16
+        self.nbytes = off
+
+    def views(self, buf):
+        return {k: buf[off:off + n].view(dt).view(shape) for k, off, n, dt, shape in self.fields}
+
+    def pack_pool(self, stacked):
+        P = next(iter(stacked.values())).shape[0]
+        out = torch.zeros((P, self.nbytes), dtype=torch.uint8)
+        for k, off, n, dt, shape in self.fields:
+            out[:, off:off + n] = stacked[k].contiguous().view(P, -1).view(torch.uint8).view(P, n)
+        return out
+
+
 # ======================================================================================
 # our arm
 # ======================================================================================
@@ -251,10 +273,13 @@ def run_ours(args, rank, world, local_rank):
         # inside a timed region that fits the pool) into the graph's input buffers, inside the timed region; L2 is
         # flushed once before the region (steps overlap, so it cannot be flushed between them).
         S, P = max(1, args.streams), max(args.pool, 2 * max(1, args.streams))
-        pool_host = {k: v.pin_memory() for k, v in batch_variants(b0, P, seed=4242 + rank).items()}
-        pool_dev = {k: v.to(dev) for k, v in pool_host.items()}
-        pipes = [pipe] + [GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64).capture(
-            dev_in, warmup=3) for _ in range(S - 1)]
+        variants = batch_variants(b0, P, seed=4242 + rank)
+        packing = Packing({k: variants[k][0] for k in dev_in})
+        pool_host = packing.pack_pool(variants).pin_memory()          # [P, nbytes] uint8, one row = one batch
+        pool_dev = pool_host.to(dev)
+        packed = [torch.zeros(packing.nbytes, dtype=torch.uint8, device=dev) for _ in range(S)]
+        pipes = [GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64).capture(
+            dev_in, warmup=3, static=packing.views(packed[i])) for i in range(S)]
         streams = [torch.cuda.Stream() for _ in range(S)]
         out_host = torch.empty((args.steps + args.warmup, G, 1), dtype=torch.float32).pin_memory()
 
@@ -264,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
                 st.wait_stream(main)
             for i in range(k):
                 with torch.cuda.stream(streams[i % S]):
-                    pipes[i % S].load({key: val[(start + i) % P] for key, val in src.items()})
+                    packed[i % S].copy_(src[(start + i) % P], non_blocking=True)      # the step's inputs: one copy
                     o = pipes[i % S].replay()
                     if d2h:
                         out_host[i].copy_(o, non_blocking=True)
@@ -284,10 +309,10 @@ def run_ours(args, rank, world, local_rank):
 
         # the pooled batches go through the same captured step: check two of them against the eager step
         for v in (1, P - 1):
-            tv = {key: val[v].clone() for key, val in pool_dev.items()}
+            tv = {key: variants[key][v].to(dev) for key in dev_in}
             with torch.no_grad():
                 exp_v = pipe.step(tv).clone()
-            pipes[-1].load(tv)
+            packed[-1].copy_(pool_dev[v])
             got_v = pipes[-1].replay().clone()
             torch.cuda.synchronize()
             assert torch.allclose(got_v, exp_v, atol=1e-5, rtol=1e-5), 'pooled batch: captured step differs from eager step'
@@ -296,7 +321,7 @@ def run_ours(args, rank, world, local_rank):
         # read back to the host (D2H inside the region); same S streams
         ms_e2e = timed_region(pool_host, True)
         assert bool(torch.isfinite(out_host[:args.steps]).all())
-    h2d = sum(v[0].numel() * v[0].element_size() for v in pool_host.values())
+    h2d = packing.nbytes
     d2h = out_host[0].numel() * out_host.element_size()
 
     if dist_on:
@@ -312,36 +337,36 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and not args.no_sweep:
         try:
             concurrent = []
-            for S in (2, 4, 12):
-                pipes = [pipe] + [GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64).capture(
-                    dev_in, warmup=3) for _ in range(S - 1)]
-                streams = [torch.cuda.Stream() for _ in range(S)]
-                K = max(args.steps, 40)
-                for p_ in pipes:
+            for S2 in (2, 4, 12):
+                pipes2 = [pipe] + [GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64).capture(
+                    dev_in, warmup=3) for _ in range(S2 - 1)]
+                streams2 = [torch.cuda.Stream() for _ in range(S2)]
+                K2 = max(args.steps, 40)
+                for p_ in pipes2:
                     p_.load(dev_in)
 
-                def run(k):
+                def run2(k):
                     main = torch.cuda.current_stream()
-                    for st in streams:
+                    for st in streams2:
                         st.wait_stream(main)
                     for i in range(k):
-                        with torch.cuda.stream(streams[i % S]):
-                            pipes[i % S].replay()
-                    for st in streams:
+                        with torch.cuda.stream(streams2[i % S2]):
+                            pipes2[i % S2].replay()
+                    for st in streams2:
                         main.wait_stream(st)
-                run(2 * S)
+                run2(2 * S2)
                 torch.cuda.synchronize()
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                run(K)
+                run2(K2)
                 e1.record()
                 torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1)
-                ok = all(torch.allclose(p_._out, ref_out, atol=1e-5, rtol=1e-5) for p_ in pipes)
-                concurrent.append({'streams': S, 'steps': K, 'graphs_per_s': K * G / (ms * 1e-3), 'ms_per_step': ms / K,
+                ms2 = e0.elapsed_time(e1)
+                ok = all(torch.allclose(p_._out, ref_out, atol=1e-5, rtol=1e-5) for p_ in pipes2)
+                concurrent.append({'streams': S2, 'steps': K2, 'graphs_per_s': K2 * G / (ms2 * 1e-3), 'ms_per_step': ms2 / K2,
                                    'outputs_match': bool(ok)})
-                del pipes
+                del pipes2
         except Exception as ex:
             concurrent = [{'error': repr(ex)[:200]}]
 
@@ -388,9 +413,10 @@ def run_ours(args, rank, world, local_rank):
                                           f'{N_LAYERS} launches of a step',
                 'achieved': scatter_bytes(N, E) / t_sc / 1e9, 'peak': peak, 'unit': 'GB/s',
                 'frac': scatter_bytes(N, E) / t_sc / 1e9 / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 launches of one step, from the
-                # committed capture profiles/r1_ncu_scatter_b128.txt (ncu --set full, B=128): 0.29 MB (layer 0) and
-                # 3 x 3.20 MB read, 0 B written (the 1.5 MB S output stays in the 126 MB L2)
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 launches of one step (ncu --set full,
+                # B=128): layers >= 1 (p1_tight_kernel) 3.20 MB read, 0 B written -- the 1.5 MB S output stays in the 126 MB
+                # L2 (profiles/r1e_ncu_tight_scatter_b128.txt); layer 0: 0.29 MB, measured before the column grouping
+                # (profiles/r1_ncu_scatter_b128.txt), i.e. an upper bound for the grouped form
                 'traffic': (0.2944e6 + 3 * 3.203328e6) / 4 if (B == 128 and N_LAYERS == 4) else None,
                 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': scatter_bytes(N, E), 'avg_launch_us': t_sc * 1e6,
@@ -452,8 +478,8 @@ def run_ours(args, rank, world, local_rank):
                               'achieved': scatter_bytes(nl, el) / tl / 1e9, 'peak': peak, 'unit': 'GB/s',
                               'frac': scatter_bytes(nl, el) / tl / 1e9 / peak, 'avg_launch_us': tl * 1e6,
                               'algorithmic_bytes_per_launch': scatter_bytes(nl, el),
-                              'traffic': 'ncu --set full at B=32,768 (profiles/r1_ncu_scatter_idx_b32768.txt): dram '
-                                         'read+write 1.16 GB per identifier-free launch vs 1.18 GB algorithmic'}
+                              'traffic': 'ncu --set full at B=131,072 (profiles/r1d_ncu_tight_scatter_b131072.txt): dram '
+                                         'read 3.18 GB + write 1.53 GB per identifier-free launch vs 4.72 GB algorithmic'}
             except Exception as ex:
                 roof_large = {'error': repr(ex)[:200]}
         cpu = cpu_baseline(pool[0], sds_oracle(), encoder, model, budget_s=12.0)
@@ -485,7 +511,7 @@ def run_ours(args, rank, world, local_rank):
                                       'LATENCY of a step; `value` keeps `streams` steps on different batches in flight'},
             'e2e': {'value': e2e_value, 'unit': 'graphs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': int(my_launches_per_step) * args.steps,     # our kernels; + 6 input copies per step
+            'gpu_launches': int(my_launches_per_step) * args.steps,     # our kernels; + 1 packed input copy per step
             'gpu_launches_per_step': int(my_launches_per_step),
             'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep, 'scatter_kernels': scatter_kernels,
             'roofline_large_batch': roof_large, 'torch_eager_gpu': eager,

@@ -95,8 +95,15 @@ class GSNPipeline:
         return self.model(data)
 
     # -- CUDA-graph capture of the whole step -------------------------------------
-    def capture(self, example: Dict[str, torch.Tensor], warmup: int = 3):
-        self._static = {k: v.clone() for k, v in example.items()}
+    def capture(self, example: Dict[str, torch.Tensor], warmup: int = 3, static: Optional[Dict[str, torch.Tensor]] = None):
+        """static: optional pre-allocated input buffers to capture on (e.g. views into ONE packed buffer, so that a
+        step's inputs arrive with a single copy); they are filled from `example`"""
+        if static is not None:
+            for k, v in example.items():
+                static[k].copy_(v)
+            self._static = static
+        else:
+            self._static = {k: v.clone() for k, v in example.items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
