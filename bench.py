@@ -482,9 +482,10 @@ def run_ours(args, rank, world, local_rank):
                                          'read 3.18 GB + write 1.53 GB per identifier-free launch vs 4.72 GB algorithmic'}
             except Exception as ex:
                 roof_large = {'error': repr(ex)[:200]}
-        cpu = cpu_baseline(pool[0], sds_oracle(), encoder, model, budget_s=12.0)
+        # reported baselines: rank 0 at N=1 only (the multi-GPU runs of the scaling sweep stay short)
+        cpu = cpu_baseline(pool[0], sds_oracle(), encoder, model, budget_s=12.0) if world == 1 else None
         eager = None
-        if not args.no_sweep:
+        if not args.no_sweep and world == 1:
             try:
                 ids_dev = counting.count_batch(dev_in['edge_index'], dev_in['node_ptr'], sds, False, 'local',
                                                max_nodes_per_graph=64)

@@ -168,6 +168,24 @@ class FlatDataset:
         standing in for torch_geometric.data.Data (PyG is absent; the attribute names and tensors are the same)"""
         torch.save((self.to_list(), self.meta.get('num_classes'), self.meta.get('orbit_partition_sizes')), path)
 
+    # ------------------------------------------------------------------ multi-GPU: contiguous shards of graphs
+    def shard(self, world: int, rank: int, balance: str = 'edges') -> 'FlatDataset':
+        """the contiguous range of graphs owned by `rank` (balanced by edge or node count, distributed.shard_ranges);
+        both hot paths shard by graph, so nothing is exchanged between shards"""
+        from .distributed import shard_ranges
+        w = (self.edge_ptr[1:] - self.edge_ptr[:-1]) if balance == 'edges' else (self.node_ptr[1:] - self.node_ptr[:-1])
+        g0, g1 = shard_ranges(w.tolist(), world)[rank]
+        n0, n1, e0, e1 = int(self.node_ptr[g0]), int(self.node_ptr[g1]), int(self.edge_ptr[g0]), int(self.edge_ptr[g1])
+        kinds = self.kinds()
+        t = {}
+        for k, v in self.tensors.items():
+            if k == 'edge_index':
+                t[k] = v[:, e0:e1]
+            else:
+                lo, hi = {'node': (n0, n1), 'edge': (e0, e1), 'graph': (g0, g1)}[kinds[k]]
+                t[k] = v[lo:hi]
+        return FlatDataset(t, self.node_ptr[g0:g1 + 1] - n0, self.edge_ptr[g0:g1 + 1] - e0, {**self.meta, 'kinds': kinds})
+
     # ------------------------------------------------------------------ collate by index arithmetic
     def batch(self, indices) -> Batch:
         """PyG DataLoader collate of the graphs `indices` (int64 tensor / list), on the device the dataset is on"""

@@ -102,3 +102,45 @@ def test_prepare_graphs_matches_per_graph_oracle(scope):
                                                         directed=False))) for sd in sds_o], 1).long()
         assert torch.equal(d.identifiers, exp)
     assert float(out[2].edge_features.min()) >= 0          # the self-loop rows are gone
+
+
+def test_shards_partition_the_dataset():
+    graphs = _graphs(4, n_graphs=11)
+    ds = FlatDataset.from_list(graphs, kinds={'identifiers': 'edge'})
+    for world in (1, 2, 3, 16):
+        seen = []
+        for rank in range(world):
+            sh = ds.shard(world, rank)
+            seen += sh.to_list()
+            assert int(sh.node_ptr[0]) == 0 and int(sh.edge_ptr[0]) == 0
+        assert len(seen) == len(graphs)
+        for a, b in zip(graphs, seen):
+            for k in ('x', 'edge_index', 'edge_features', 'identifiers', 'y'):
+                assert torch.equal(getattr(a, k), getattr(b, k)), (world, k)
+
+
+def test_bench_batch_variants_and_packing():
+    """bench.py helpers: the pooled batches keep the shapes of the base batch (CUDA graphs need static shapes),
+    hold the same graphs in another order, and survive the single-buffer packing bit for bit"""
+    import bench
+    b = bench.build_batches(16, 1, seed0=3)[0]
+    v = bench.batch_variants(b, 3, seed=1)
+    keys = ('edge_index', 'node_ptr', 'x', 'edge_features', 'batch', 'degrees')
+    for i in range(3):
+        ei, nptr, bt = v['edge_index'][i].numpy(), v['node_ptr'][i].numpy(), v['batch'][i].numpy()
+        assert ei.shape == b['edge_index'].shape and sorted(np.diff(nptr)) == sorted(np.diff(b['node_ptr']))
+        g0 = np.searchsorted(nptr, ei[0], side='right') - 1
+        g1 = np.searchsorted(nptr, ei[1], side='right') - 1
+        assert (g0 == g1).all() and (bt[ei[0]] == g0).all()
+        pairs = set(map(tuple, ei.T.tolist()))
+        assert all((q, p) in pairs for p, q in pairs)                      # still symmetric
+        assert (v['degrees'][i].numpy() == np.bincount(ei[0], minlength=int(nptr[-1]))).all()
+    assert not np.array_equal(v['edge_index'][0].numpy(), v['edge_index'][1].numpy())
+    pk = bench.Packing({k: v[k][0] for k in keys})
+    pool = pk.pack_pool(v)
+    buf = torch.zeros(pk.nbytes, dtype=torch.uint8)
+    views = pk.views(buf)
+    for i in range(3):
+        buf.copy_(pool[i])
+        for k in keys:
+            assert torch.equal(views[k], v[k][i]), k

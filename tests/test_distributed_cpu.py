@@ -95,3 +95,44 @@ def test_two_rank_gloo_allreduce_broadcast_and_vocabulary():
         assert p.exitcode == 0
     for rank, ok_grad, ok_bcast, ok_voc in res:
         assert ok_grad and ok_bcast and ok_voc, (rank, ok_grad, ok_bcast, ok_voc)
+
+
+def _dataset_worker(rank, world, port, path, q):
+    """N>1 host path of the dataset cache: every rank loads the flat cache, takes its shard, collates its own
+    mini-batches and contributes to the data-set-wide identifier vocabulary (the one exchange COUNT sharding needs)"""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from gsn_b200.dataset import FlatDataset
+        ds = FlatDataset.load(path)
+        sh = ds.shard(world, rank)
+        counts = torch.tensor([len(sh), sh.num_nodes, sh.num_edges])
+        dist.all_reduce(counts)
+        ok_partition = counts.tolist() == [len(ds), ds.num_nodes, ds.num_edges]
+        voc = gd.global_unique_per_column(sh.tensors['identifiers'])
+        full = [torch.unique(ds.tensors['identifiers'][:, c]) for c in range(ds.tensors['identifiers'].shape[1])]
+        ok_vocab = all(torch.equal(a, b) for a, b in zip(voc, full))
+        b = sh.batch(list(range(min(3, len(sh)))))
+        ok_batch = int(b.node_ptr[-1]) == b.x.shape[0] and (b.edge_index.numel() == 0 or int(b.edge_index.max()) < b.x.shape[0])
+        q.put((rank, ok_partition, ok_vocab, ok_batch))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_dataset_cache(tmp_path):
+    from gsn_b200.dataset import FlatDataset
+    from tests.test_dataset import _graphs
+    path = os.path.join(tmp_path, 'cache.pt')
+    FlatDataset.from_list(_graphs(7, n_graphs=13), kinds={'identifiers': 'edge'}).save(path)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dataset_worker, args=(r, 2, port, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, *oks in res:
+        assert all(oks), (rank, oks)
