@@ -414,10 +414,10 @@ def run_ours(args, rank, world, local_rank):
                 'achieved': scatter_bytes(N, E) / t_sc / 1e9, 'peak': peak, 'unit': 'GB/s',
                 'frac': scatter_bytes(N, E) / t_sc / 1e9 / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 launches of one step (ncu --set full,
-                # B=128): layers >= 1 (p1_tight_kernel) 3.20 MB read, 0 B written -- the 1.5 MB S output stays in the 126 MB
-                # L2 (profiles/r1e_ncu_tight_scatter_b128.txt); layer 0: 0.29 MB, measured before the column grouping
-                # (profiles/r1_ncu_scatter_b128.txt), i.e. an upper bound for the grouped form
-                'traffic': (0.2944e6 + 3 * 3.203328e6) / 4 if (B == 128 and N_LAYERS == 4) else None,
+                # B=128): layer 0 (tab_tight_kernel, grouped columns) 0.182 MB read (profiles/r1g_ncu_tab_tight_b128.txt);
+                # layers >= 1 (p1_tight_kernel) 3.20 MB read (profiles/r1e_ncu_tight_scatter_b128.txt); 0 B written in both
+                # -- the 1.5 MB S output stays in the 126 MB L2
+                'traffic': (0.182272e6 + 3 * 3.200768e6) / 4 if (B == 128 and N_LAYERS == 4) else None,
                 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': scatter_bytes(N, E), 'avg_launch_us': t_sc * 1e6,
                 'launches_per_step': prof['general_edge'][1],
