@@ -754,9 +754,10 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
     int BN = p.Nout > 128 ? 256 : (p.Nout > 64 ? 128 : 64);
     const int64_t m_tiles = ceil_div(p.M, TC_BM);
     if (m_tiles * ceil_div(p.Nout, BN) < kNumSMs / 2 && p.Nout >= 32) BN = 32;
+    static const int tc_mode = getenv("GSN_TC_MODE") ? atoi(getenv("GSN_TC_MODE")) : 0;    // experiment switch, read once
     TcEpilogue ep{p.bias, p.row_scale, p.row_vec, p.tab, p.scale, p.shift, p.tab_idx, p.C,
                   p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate, (long long *)g_tc_debug,
-                  getenv("GSN_TC_MODE") ? atoi(getenv("GSN_TC_MODE")) : 0};
+                  tc_mode};
     CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
     int rc;
     if ((rc = make_map(&mW_hi, d_Whi, p.Nout, K, K, BN))) return rc;
