@@ -214,3 +214,32 @@ class FlatDataset:
                 out[k] = v[idx]
         out['batch'], out['node_ptr'], out['edge_ptr'], out['num_graphs'] = gid_n, node_ptr, edge_ptr, int(idx.numel())
         return Batch(**out)
+
+
+class FlatLoader:
+    """The DataLoader of main.py:243-258 (`DataLoader(dataset, batch_size=, shuffle=, worker_init_fn=...)` with PyG's
+    collate) over a FlatDataset: an epoch is a permutation of graph ids cut into batches, every batch one
+    `FlatDataset.batch` call on the device the data set lives on -- no worker processes, no per-graph objects.
+    shuffle draws `torch.randperm(n, generator=generator)` per epoch (torch's RandomSampler does the same after the
+    DataLoader has consumed one draw for its base seed, so the permutations differ for equal seeds); the last short
+    batch is kept unless drop_last."""
+
+    def __init__(self, dataset: FlatDataset, batch_size: int = 1, shuffle: bool = False, drop_last: bool = False,
+                 generator: Optional[torch.Generator] = None):
+        if batch_size < 1:
+            raise ValueError('batch_size must be positive')
+        self.dataset, self.batch_size, self.shuffle, self.drop_last, self.generator = dataset, int(batch_size), shuffle, drop_last, generator
+
+    def __len__(self):
+        n = len(self.dataset)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = len(self.dataset)
+        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
+        for lo in range(0, n, self.batch_size):
+            idx = order[lo:lo + self.batch_size]
+            if self.drop_last and idx.numel() < self.batch_size:
+                return
+            yield self.dataset.batch(idx)
+

@@ -144,3 +144,26 @@ def test_bench_batch_variants_and_packing():
         buf.copy_(pool[i])
         for k in keys:
             assert torch.equal(views[k], v[k][i]), k
+
+
+def test_flat_loader_batches_equal_collate_over_the_same_order():
+    """sequential order == torch DataLoader(list, collate_fn=collate); shuffled order == collate over randperm(seed)"""
+    from torch.utils.data import DataLoader
+    from gsn_b200.dataset import FlatLoader
+    graphs = _graphs(5, n_graphs=10)
+    ds = FlatDataset.from_list(graphs, kinds={'identifiers': 'edge'})
+    keys = ('x', 'edge_index', 'edge_features', 'identifiers', 'y', 'batch', 'node_ptr')
+    for drop_last, bs in ((False, 4), (True, 4), (False, 10), (False, 1)):
+        ref = list(DataLoader(graphs, batch_size=bs, shuffle=False, drop_last=drop_last, collate_fn=collate))
+        got = list(FlatLoader(ds, batch_size=bs, drop_last=drop_last))
+        assert len(ref) == len(got) == len(FlatLoader(ds, bs, False, drop_last))
+        for a, b in zip(ref, got):
+            for k in keys:
+                assert torch.equal(getattr(a, k), getattr(b, k)), (k, drop_last, bs)
+    order = torch.randperm(10, generator=torch.Generator().manual_seed(9)).tolist()
+    got = list(FlatLoader(ds, batch_size=3, shuffle=True, generator=torch.Generator().manual_seed(9)))
+    assert len(got) == 4
+    for i, b in enumerate(got):
+        exp = collate([graphs[j] for j in order[3 * i:3 * i + 3]])
+        for k in keys:
+            assert torch.equal(getattr(exp, k), getattr(b, k)), (k, i)
