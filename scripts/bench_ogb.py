@@ -3,6 +3,10 @@
 B = 512 synthetic molhiv-shaped graphs: COUNT time and one TRAINING step (forward + backward + Adam).
 
     python scripts/bench_ogb.py                    # this package on cuda:0
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_ogb.py
+                                                   # N GPUs: every rank trains on its own B graphs (weak scaling), weights
+                                                   # broadcast from rank 0, ONE flat-buffer NCCL all-reduce of the gradients
+                                                   # per step (the only collective of the system; BatchNorm stays per shard)
     python scripts/bench_ogb.py --impl reference   # the unmodified reference model on the host CPU (needs /root/reference)
 """
 import argparse
@@ -51,8 +55,14 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--id-cap', type=int, default=64, help='identifier embedding rows per column (counts are clamped)')
     a = ap.parse_args()
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if world > 1 and a.impl == 'ours':
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
     from gsn_b200.synthetic import zinc_like_batch
-    b = zinc_like_batch(a.batch, seed=21, mean_nodes=25.5, sd_nodes=12.0, min_nodes=2, max_nodes=222)
+    b = zinc_like_batch(a.batch, seed=21 + rank, mean_nodes=25.5, sd_nodes=12.0, min_nodes=2, max_nodes=222)
     N, E = int(b['node_ptr'][-1]), int(b['edge_index'].shape[1])
     rng = np.random.default_rng(5)
     x = torch.from_numpy(np.stack([rng.integers(0, d, N) for d in ATOM], 1))
@@ -72,7 +82,8 @@ def main():
     if a.impl == 'ours':
         from gsn_b200 import counting, patterns
         from gsn_b200.network import GNN_OGB
-        dev = torch.device('cuda', 0)
+        dev = torch.device('cuda', local)
+        torch.cuda.set_device(dev)
         torch.backends.cuda.matmul.allow_tf32 = False
         sds = patterns.make_subgraph_dicts(els, 'global')
         ei_d = ei.to(dev)
@@ -99,11 +110,17 @@ def main():
         data.identifiers, data.degrees, data.node_ptr = ids, torch.from_numpy(b['degrees']).to(dev), node_ptr.to(dev)
         yd = y.to(dev)
         opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        if world > 1:
+            from gsn_b200 import distributed as gd
+            gd.broadcast_parameters(model, src=0)
+        params = [p_ for p_ in model.parameters()]
 
         def step():
             opt.zero_grad(set_to_none=True)
             loss = torch.nn.functional.binary_cross_entropy_with_logits(model(data), yd)
             loss.backward()
+            if world > 1:
+                gd.allreduce_gradients(params)          # one flat fp32 buffer, averaged
             opt.step()
             return loss
         for _ in range(a.warmup):
@@ -118,9 +135,13 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps
-        res.update(train_step_ms=ms, graphs_per_s=a.batch / (ms * 1e-3), loss=float(loss),
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            ms = float(tt[0])
+        res.update(n_gpus=world, train_step_ms=ms, graphs_per_s=world * a.batch / (ms * 1e-3), loss=float(loss),
                    gsn_kernel_launches_per_step=(_lib.launch_count() - l0) / a.steps,
-                   count_plus_step_graphs_per_s=a.batch / ((ms + res['count_ms']) * 1e-3))
+                   count_plus_step_graphs_per_s=world * a.batch / ((ms + res['count_ms']) * 1e-3))
         model.eval()
         with torch.no_grad():
             for _ in range(2):
@@ -158,7 +179,11 @@ def main():
         res.update(train_step_ms=ms, graphs_per_s=a.batch / (ms * 1e-3), cores=torch.get_num_threads(),
                    note='unmodified reference model (models_graph_classification_ogb_original.py) on the host CPU, PyTorch '
                         'threads = cores; identifiers random (graph-tool absent, COUNT not timed)')
-    print(json.dumps(res))
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1 and a.impl == 'ours':
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':
