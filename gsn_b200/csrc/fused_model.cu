@@ -1,0 +1,758 @@
+// Whole-model fused inference forward of GNNSubstructures ('general' message kind) for sm_100a: ONE persistent
+// kernel runs every layer of models_graph_classification.py:204-247 for a tile of WHOLE graphs.
+//
+// A PyG batch is a block-diagonal graph: a row tile that holds whole graphs (<= 128 nodes) never reads
+// a row outside itself, so nothing but the inputs and the per-graph readout has to touch HBM -- the per-layer
+// activations x, the split first Linear P = (P_i | P_j) of msg_fn, the neighbour sums S and the hidden rows H of
+// update_fn live in shared memory / tensor memory from the first layer to the readout:
+//
+//   per layer (GSN_edge_sparse.py:111-166 + models_misc.py:52-59, re-associated as in gsn_b200/fused.py):
+//     P_j = x Wxj^T            tcgen05 -> TMEM -> smem (fp32, gathered by neighbours)
+//     P_i = x Wxi^T + shift    tcgen05 -> TMEM (read in place by the row's own thread)
+//     Ux  = x U1x^T            tcgen05 -> TMEM (kept until the update epilogue)
+//     S_i = sum_e act(P_i[i] + P_j[nbr e] + sum_g Te[rows_g(e)])        registers, smem gathers
+//     H   = act((Ux + S Wf^T + deg vf + c1 [+ Tu[x_i]]) su + tu)        tcgen05 + epilogue
+//     x'  = act((H U2^T + c2) sm + tm)                                  tcgen05 + epilogue (+ per-graph readout)
+//
+// Tensor-core arithmetic: fp32 parity (1e-5) needs ~21 mantissa bits.  fp16 has the SAME 11-bit mantissa as tf32 at
+// twice the MMA rate and half the operand bytes, so every product is 3 x fp16 (a_hi w_hi + a_lo w_hi + a_hi w_lo)
+// with EXACT power-of-two scaling that removes the range problem: each activation row is scaled so that its largest
+// element lies in [2^14, 2^15) (dynamic, in the epilogue that produces the operand), each weight row likewise (static,
+// host side); the epilogue multiplies the two exponents back.  Elements 2^17 below their row's maximum lose low bits
+// of the lo part only (absolute error <= 2^-39 of the row maximum).  The two correction terms accumulate in their own
+// TMEM accumulator (the tensor core truncates when it adds into fp32, see tc_linear.cu).
+//
+// Warp roles (384 threads, 1 CTA / SM):  warp 0 TMA producer (weight ring), warp 1 MMA issuer, warp 2 TMEM alloc,
+// warps 4..11 compute (thread = (row, half of the columns): epilogues, message phase, operand conversion).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace gsn {
+
+constexpr int FM_MAX_LAYERS = GSN_FUSED_MAX_LAYERS;
+constexpr int FM_ROWS = 128;
+constexpr int FM_NV = 9;            // per-layer column vectors
+enum { V_CJ = 0, V_CI, V_SHIFT, V_CU, V_CF, V_CV, V_CB, V_C2S, V_C2B };
+constexpr int FM_TE_SMALL = 8192;   // bytes of the always-available edge-table staging area
+constexpr int FM_COMPUTE_THREADS = 256;
+
+struct FmLayer {
+    const int32_t *node_rows; const float *Tn;
+    const int32_t *tu_rows; const float *Tu;
+    const int32_t *edge_rows; const float *Te;
+    const float *vec; float *pooled; float *x_out;
+    int32_t n_node_cols, tu_stride, n_edge_cols, te_rows, has_dense, mat0, act_msg, act_upd, act_out, pool;
+};
+
+struct FmParams {
+    FmLayer layer[FM_MAX_LAYERS];
+    int32_t n_layers;
+    const int32_t *rowptr, *nbr;
+    const int64_t *node_ptr;
+    const float *x0;
+    int32_t x0_ld, x0_d;
+    int32_t G, unit, n_units;
+    int32_t *status;
+};
+
+__device__ __noinline__ float fm_act_slow(float v, int act) {
+    return act == 1 ? (v > 0.0f ? v : expm1f(v)) : tanhf(v);
+}
+__device__ __forceinline__ float fm_act(float v, int act) {
+    if (act == 0) return fmaxf(v, 0.f);
+    if (act == 3) return v;
+    return fm_act_slow(v, act);
+}
+
+__device__ __forceinline__ void fm_tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t fm_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void fm_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void fm_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// mbarrier wait with a watchdog: a protocol error traps (the launch fails with an error the host reports) instead of
+// hanging the GPU.  `what` identifies the wait site in the message.
+__device__ __forceinline__ void fm_wait(uint64_t *bar, uint32_t parity, int what) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done, spins = 0;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 24)) {
+            printf("fused_model_kernel: mbarrier wait %d timed out (block %d thread %d parity %u)\n", what, blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    } while (!done);
+}
+
+__device__ __forceinline__ void fm_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void fm_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// main + correction accumulator of one 32-column chunk
+template <int D>
+__device__ __forceinline__ void fm_acc_ld(uint32_t acc_base, int col0, float (&v)[32]) {
+    float q[32];
+    fm_tmem_ld32(acc_base + (uint32_t)col0, v);
+    fm_tmem_ld32(acc_base + (uint32_t)(D + col0), q);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += q[j];
+}
+
+// byte offset of 16-byte chunk q of row `row` in an fp32 [rows, D] shared-memory matrix whose chunks are XOR-swizzled
+// inside every 128-byte group (rows that differ in their low 3 bits hit different banks when read at the same column)
+template <int D>
+__device__ __forceinline__ uint32_t fm_swz(int row, int q) {
+    return (uint32_t)row * (uint32_t)(D * 4) + (uint32_t)(((q & ~7) | ((q ^ row) & 7)) << 4);
+}
+
+// first graph after the tile that starts at graph g0 (whole graphs, <= 128 rows, <= 32 graphs, inside the unit)
+__device__ __forceinline__ int fm_tile_end(const int64_t *node_ptr, int g0, int gend, int lane) {
+    const int64_t base = __ldg(node_ptr + g0);
+    const int g = g0 + 1 + lane;
+    const bool ok = g <= gend && (__ldg(node_ptr + g) - base) <= FM_ROWS;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    const int cnt = (m == 0xffffffffu) ? 32 : (__ffs((int)~m) - 1);
+    return g0 + cnt;
+}
+
+__device__ __forceinline__ void fm_bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int D>
+struct FmCfg {
+    static constexpr int KS = D / 64;                       // 64-half (128-byte) k-slabs per operand
+    static constexpr int SLAB = FM_ROWS * 128;              // bytes of one A k-slab (hi or lo)
+    static constexpr int A_BYTES = 2 * KS * SLAB;           // hi slabs | lo slabs
+    static constexpr int PJ_BYTES = FM_ROWS * D * 4;
+    static constexpr int STAGE = D * 128;                   // one weight k-slab (hi or lo): D rows x 128 bytes
+    static constexpr int NST = D == 128 ? 5 : 8;
+    static constexpr int VEC_BYTES = FM_NV * D * 4;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_PJ = OFF_A + A_BYTES;
+    static constexpr int OFF_RING = OFF_PJ + PJ_BYTES;
+    static constexpr int OFF_TE = OFF_RING + NST * STAGE;
+    static constexpr int OFF_VEC = OFF_TE + FM_TE_SMALL;
+    static constexpr int OFF_RMAX = OFF_VEC + VEC_BYTES;
+    static constexpr int SMEM = OFF_RMAX + 2 * FM_ROWS * 4 + 1024;     // + alignment slack
+    static constexpr int CPT = D / 64;                      // 32-column chunks per compute thread
+    static constexpr uint32_t TMEM_COLS = 4 * D;            // acc0 (main|corr) | acc1 (main|corr)
+};
+
+template <int D>
+__global__ void __launch_bounds__(384, 1)
+fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                   const __grid_constant__ FmParams P) {
+    using C = FmCfg<D>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t w_full[C::NST], w_empty[C::NST], a_ready, acc_full[2], acc1_free;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sA = smem_u32(sm + C::OFF_A), sPJ = smem_u32(sm + C::OFF_PJ), sRING = smem_u32(sm + C::OFF_RING);
+    const uint32_t sTE = smem_u32(sm + C::OFF_TE);
+    float *vecs = reinterpret_cast<float *>(sm + C::OFF_VEC);
+    float *rmax = reinterpret_cast<float *>(sm + C::OFF_RMAX);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::NST; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        mbar_init(&a_ready, 8);
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
+        mbar_init(&acc1_free, 8);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_smem;
+    const uint32_t ACC0 = tmem, ACC1 = tmem + 2 * D;
+    const int nL = P.n_layers;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------- TMA producer: weight k-slabs in order of use
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            const int gend = min(P.G, (u + 1) * P.unit);
+            int g0 = u * P.unit;
+            while (g0 < gend) {
+                int g1 = fm_tile_end(P.node_ptr, g0, gend, lane);
+                if (g1 == g0) { g0 += 1; continue; }
+                if (lane == 0) {
+                    for (int l = 0; l < nL; ++l) {
+                        const int nm = P.layer[l].has_dense ? 5 : 2;
+                        for (int m = 0; m < nm; ++m) {
+                            const int wrow = (P.layer[l].mat0 + m) * D;
+                            for (int s = 0; s < C::KS; ++s) {
+#pragma unroll 1
+                                for (int part = 0; part < 2; ++part, ++it) {
+                                    const uint32_t st = it % C::NST, ph = (it / C::NST) & 1;
+                                    fm_wait(&w_empty[st], ph ^ 1, 1);
+                                    mbar_arrive_expect_tx(&w_full[st], C::STAGE);
+                                    fm_tma_load_2d(sm + C::OFF_RING + st * C::STAGE, part == 0 ? &tmWhi : &tmWlo, s * 64, wrow,
+                                                   &w_full[st]);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                g0 = g1;
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------- MMA issuer
+        // instruction descriptor: D = F32, A = B = F16, both K-major, N = D, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(FM_ROWS >> 4) << 24);
+        uint32_t it = 0, n_aready = 0, n_free = 0;
+        // one GEMM: acc (main | corr) = A(smem operand buffer) x W(ring)^T
+        auto gemm = [&](uint32_t acc) {
+            for (int s = 0; s < C::KS; ++s) {
+                const uint64_t a_hi = fm_desc(sA + s * C::SLAB), a_lo = fm_desc(sA + (C::KS + s) * C::SLAB);
+                {   // hi weights: main += a_hi w_hi ; corr += a_lo w_hi
+                    const uint32_t st = it % C::NST, ph = (it / C::NST) & 1;
+                    fm_wait(&w_full[st], ph, 2);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t w = fm_desc(sRING + st * C::STAGE);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t first = (s > 0 || k > 0) ? 1u : 0u;
+                        fm_mma_f16(acc, a_hi + 2 * k, w + 2 * k, idesc, first);
+                        fm_mma_f16(acc + D, a_lo + 2 * k, w + 2 * k, idesc, first);
+                    }
+                    fm_commit(&w_empty[st]);
+                    ++it;
+                }
+                {   // lo weights: corr += a_hi w_lo
+                    const uint32_t st = it % C::NST, ph = (it / C::NST) & 1;
+                    fm_wait(&w_full[st], ph, 3);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t w = fm_desc(sRING + st * C::STAGE);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) fm_mma_f16(acc + D, a_hi + 2 * k, w + 2 * k, idesc, 1u);
+                    fm_commit(&w_empty[st]);
+                    ++it;
+                }
+            }
+        };
+        auto wait_aready = [&]() {
+            fm_wait(&a_ready, n_aready & 1, 4);
+            ++n_aready;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        };
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            const int gend = min(P.G, (u + 1) * P.unit);
+            int g0 = u * P.unit;
+            while (g0 < gend) {
+                int g1 = fm_tile_end(P.node_ptr, g0, gend, lane);
+                if (g1 == g0) { g0 += 1; continue; }
+                if (lane == 0) {
+                    for (int l = 0; l < nL; ++l) {
+                        if (P.layer[l].has_dense) {
+                            wait_aready();                       // x operand in place, both accumulators drained
+                            gemm(ACC1);                          // P_j
+                            fm_commit(&acc_full[1]);
+                            gemm(ACC0);                          // P_i
+                            fm_commit(&acc_full[0]);
+                            fm_wait(&acc1_free, n_free & 1, 5);   // P_j copied out of ACC1
+                            ++n_free;
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            gemm(ACC1);                          // Ux = x U1x^T
+                            fm_commit(&acc_full[1]);
+                        }
+                        wait_aready();                           // S operand in place, P_i (ACC0) consumed
+                        gemm(ACC0);                              // S Wf^T
+                        fm_commit(&acc_full[0]);
+                        wait_aready();                           // H operand in place, ACC0 / ACC1 consumed
+                        gemm(ACC0);                              // H U2^T
+                        fm_commit(&acc_full[0]);
+                    }
+                }
+                __syncwarp();
+                g0 = g1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------- compute warps
+        const int cw = warp - 4;
+        const int q = cw & 3;                    // TMEM lane quarter this warp may touch (= warp % 4)
+        const int half = cw >> 2;                // which half of the columns
+        const int r = q * 32 + lane;             // tile row = TMEM lane
+        const int ct = threadIdx.x - 128;        // 0..255
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        uint32_t n_full[2] = {0, 0};
+        auto wait_acc = [&](int b) {
+            fm_wait(&acc_full[b], n_full[b] & 1, 6 + b);
+            ++n_full[b];
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        };
+        // values of this thread's CPT chunks -> fp16 (hi, lo) operand rows, scaled by the row's power of two; returns
+        // the inverse scale.  Leaves the operand visible to the tensor core and signals the MMA warp.
+        auto write_operand = [&](float (&val)[C::CPT][32]) -> float {
+            float m = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < C::CPT; ++ci)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(val[ci][j]));
+            rmax[half * FM_ROWS + r] = m;
+            fm_bar_compute();
+            m = fmaxf(rmax[r], rmax[FM_ROWS + r]);
+            int e = (int)((__float_as_uint(m) >> 23) & 0xFF);                 // biased exponent of the row maximum
+            if (e == 0) e = 127 + 14;                                          // zero / denormal row: scale 1
+            int se = 127 + 14 - (e - 127);                                     // scale = 2^(14 - (e - 127))
+            se = max(1, min(254, se));
+            const float scale = __uint_as_float((uint32_t)se << 23);
+            const float inv = __uint_as_float((uint32_t)(254 - se) << 23);    // 2^-(se-127)
+#pragma unroll
+            for (int ci = 0; ci < C::CPT; ++ci) {
+                const int col0 = (half * C::CPT + ci) * 32;
+                const int slab = col0 >> 6;
+                const int j0 = (col0 & 63) >> 3;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float a = val[ci][jj * 8 + 2 * t] * scale, b = val[ci][jj * 8 + 2 * t + 1] * scale;
+                        const __half2 h2 = __floats2half2_rn(a, b);
+                        const float2 hf = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+                        hi[t] = *reinterpret_cast<const uint32_t *>(&h2);
+                        lo[t] = *reinterpret_cast<const uint32_t *>(&l2);
+                    }
+                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)(((j0 + jj) ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + slab * C::SLAB + off), "r"(hi[0]),
+                                 "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + (C::KS + slab) * C::SLAB + off),
+                                 "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) fm_arrive(&a_ready);
+            return inv;
+        };
+
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            const int gend = min(P.G, (u + 1) * P.unit);
+            int g0 = u * P.unit;
+            while (g0 < gend) {
+                const int g1 = fm_tile_end(P.node_ptr, g0, gend, lane);
+                if (g1 == g0) {
+                    if (ct == 0) atomicOr(P.status, GSN_S_GRAPH_TOO_LARGE);
+                    g0 += 1;
+                    continue;
+                }
+                const int64_t row0 = __ldg(P.node_ptr + g0);
+                const int n_rows = (int)(__ldg(P.node_ptr + g1) - row0);
+                const bool valid = r < n_rows;
+                const int64_t grow = row0 + (valid ? r : 0);
+                const int e_begin = valid ? __ldg(P.rowptr + grow) : 0;
+                const int e_end = valid ? __ldg(P.rowptr + grow + 1) : 0;
+                const float deg = (float)(e_end - e_begin);
+                float rx_inv = 1.f;       // inverse row scale of the operand currently in the A buffer
+
+                for (int l = 0; l < nL; ++l) {
+                    const FmLayer &L = P.layer[l];
+                    // ---- per-layer constants into shared memory (previous layer's readers are past their last use:
+                    //      they arrived on a_ready after the x' epilogue; the barrier orders the overwrite)
+                    fm_bar_compute();
+                    for (int i = ct; i < FM_NV * D; i += FM_COMPUTE_THREADS) vecs[i] = __ldg(L.vec + i);
+                    // edge tables: 0 none / global, 1 small area, 2 the (still unused) operand buffer of a table-only layer
+                    int te_loc = 0;
+                    const int te_bytes = L.te_rows * D * 4;
+                    if (L.n_edge_cols > 0) {
+                        if (te_bytes <= FM_TE_SMALL) te_loc = 1;
+                        else if (!L.has_dense && te_bytes <= C::A_BYTES) te_loc = 2;
+                    }
+                    const uint32_t sTab = te_loc == 2 ? sA : sTE;
+                    if (te_loc) {
+                        const int nq = L.te_rows * (D / 4);
+                        for (int i = ct; i < nq; i += FM_COMPUTE_THREADS) {
+                            const int trow = i / (D / 4), tq = i % (D / 4);
+                            const float4 v = __ldg(reinterpret_cast<const float4 *>(L.Te) + i);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sTab + fm_swz<D>(trow, tq)), "f"(v.x),
+                                         "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                        }
+                    }
+                    if (l == 0 && L.has_dense) {
+                        // ---- dense input features: fp32 rows -> operand buffer
+                        float val[C::CPT][32];
+#pragma unroll
+                        for (int ci = 0; ci < C::CPT; ++ci) {
+                            const int col0 = (half * C::CPT + ci) * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                val[ci][j] = (valid && col0 + j < P.x0_d) ? __ldg(P.x0 + grow * P.x0_ld + col0 + j) : 0.f;
+                        }
+                        rx_inv = write_operand(val);
+                    }
+                    fm_bar_compute();          // vectors / tables staged
+
+                    // ---- P_j rows into shared memory
+                    {
+                        if (L.has_dense) wait_acc(1);
+#pragma unroll
+                        for (int ci = 0; ci < C::CPT; ++ci) {
+                            const int col0 = (half * C::CPT + ci) * 32;
+                            float v[32];
+                            if (L.has_dense) {
+                                fm_acc_ld<D>(ACC1 + lane_off, col0, v);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] *= rx_inv * vecs[V_CJ * D + col0 + j];
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                            }
+                            if (valid) {
+                                for (int c = 0; c < L.n_node_cols; ++c) {
+                                    const int trow = __ldg(L.node_rows + grow * L.n_node_cols + c);
+                                    const float4 *t4 = reinterpret_cast<const float4 *>(L.Tn + (int64_t)trow * (2 * D) + D + col0);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 t = __ldg(t4 + i);
+                                        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sPJ + fm_swz<D>(r, col0 / 4 + i)),
+                                             "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+                        }
+                        if (L.has_dense) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) fm_arrive(&acc1_free);
+                        }
+                    }
+                    fm_bar_compute();          // every row of P_j visible
+
+                    // ---- message phase: S_i = sum_e act(P_i + P_j[nbr] + sum_g Te[rows])
+                    float S[C::CPT][32];
+                    {
+                        if (L.has_dense) wait_acc(0);
+                        const int ng = L.n_edge_cols;
+                        const int act = L.act_msg;
+#pragma unroll
+                        for (int ci = 0; ci < C::CPT; ++ci) {
+                            const int col0 = (half * C::CPT + ci) * 32;
+                            float p[32];
+                            if (L.has_dense) {
+                                fm_acc_ld<D>(ACC0 + lane_off, col0, p);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    p[j] = fmaf(p[j], rx_inv * vecs[V_CI * D + col0 + j], vecs[V_SHIFT * D + col0 + j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) p[j] = vecs[V_SHIFT * D + col0 + j];
+                            }
+                            if (valid) {
+                                for (int c = 0; c < L.n_node_cols; ++c) {
+                                    const int trow = __ldg(L.node_rows + grow * L.n_node_cols + c);
+                                    const float4 *t4 = reinterpret_cast<const float4 *>(L.Tn + (int64_t)trow * (2 * D) + col0);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 t = __ldg(t4 + i);
+                                        p[4 * i] += t.x; p[4 * i + 1] += t.y; p[4 * i + 2] += t.z; p[4 * i + 3] += t.w;
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) S[ci][j] = 0.f;
+                            for (int k = e_begin; k < e_end; ++k) {
+                                const int jl = (int)((int64_t)__ldg(P.nbr + k) - row0);
+                                if ((unsigned)jl >= (unsigned)n_rows) {
+                                    atomicOr(P.status, GSN_S_CROSS_GRAPH_EDGE);
+                                    continue;
+                                }
+                                float h[32];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float4 t;
+                                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                                 : "r"(sPJ + fm_swz<D>(jl, col0 / 4 + i)));
+                                    h[4 * i] = p[4 * i] + t.x; h[4 * i + 1] = p[4 * i + 1] + t.y;
+                                    h[4 * i + 2] = p[4 * i + 2] + t.z; h[4 * i + 3] = p[4 * i + 3] + t.w;
+                                }
+                                for (int g = 0; g < ng; ++g) {
+                                    const int trow = __ldg(L.edge_rows + (int64_t)k * ng + g);
+                                    if (te_loc) {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) {
+                                            float4 t;
+                                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                                         : "r"(sTab + fm_swz<D>(trow, col0 / 4 + i)));
+                                            h[4 * i] += t.x; h[4 * i + 1] += t.y; h[4 * i + 2] += t.z; h[4 * i + 3] += t.w;
+                                        }
+                                    } else {
+                                        const float4 *t4 = reinterpret_cast<const float4 *>(L.Te + (int64_t)trow * D + col0);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) {
+                                            const float4 t = __ldg(t4 + i);
+                                            h[4 * i] += t.x; h[4 * i + 1] += t.y; h[4 * i + 2] += t.z; h[4 * i + 3] += t.w;
+                                        }
+                                    }
+                                }
+                                if (act == 0) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) S[ci][j] += fmaxf(h[j], 0.f);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) S[ci][j] += fm_act(h[j], act);
+                                }
+                            }
+                        }
+                    }
+                    // the operand buffer may be overwritten once Ux (the last GEMM reading x) has completed; a table-only
+                    // layer has no GEMM in flight, but its tables may sit in the operand buffer: write_operand's barrier
+                    // (every thread is past its message loop) orders that
+                    if (L.has_dense) wait_acc(1);
+                    const float rs_inv = write_operand(S);
+
+                    // ---- update epilogue: H = act((Ux + S Wf^T + deg vf + c1 [+ Tu]) su + tu)
+                    float rh_inv;
+                    {
+                        wait_acc(0);
+                        float H[C::CPT][32];
+                        const int act = L.act_upd;
+#pragma unroll
+                        for (int ci = 0; ci < C::CPT; ++ci) {
+                            const int col0 = (half * C::CPT + ci) * 32;
+                            fm_acc_ld<D>(ACC0 + lane_off, col0, H[ci]);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                H[ci][j] = fmaf(H[ci][j], rs_inv * vecs[V_CF * D + col0 + j],
+                                                fmaf(deg, vecs[V_CV * D + col0 + j], vecs[V_CB * D + col0 + j]));
+                            if (L.has_dense) {
+                                float uacc[32];
+                                fm_acc_ld<D>(ACC1 + lane_off, col0, uacc);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) H[ci][j] = fmaf(uacc[j], rx_inv * vecs[V_CU * D + col0 + j], H[ci][j]);
+                            }
+                            if (L.Tu && valid) {
+                                const int trow = __ldg(L.tu_rows + grow * L.tu_stride);
+                                const float4 *t4 = reinterpret_cast<const float4 *>(L.Tu + (int64_t)trow * D + col0);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 t = __ldg(t4 + i);
+                                    H[ci][4 * i] += t.x; H[ci][4 * i + 1] += t.y; H[ci][4 * i + 2] += t.z; H[ci][4 * i + 3] += t.w;
+                                }
+                            }
+                            if (act == 0) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) H[ci][j] = valid ? fmaxf(H[ci][j], 0.f) : 0.f;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) H[ci][j] = valid ? fm_act(H[ci][j], act) : 0.f;
+                            }
+                        }
+                        rh_inv = write_operand(H);
+                    }
+
+                    // ---- output epilogue: x' = act((H U2^T + c2) sm + tm), readout, next layer's operand
+                    {
+                        wait_acc(0);
+                        float X[C::CPT][32];
+                        const int act = L.act_out;
+#pragma unroll
+                        for (int ci = 0; ci < C::CPT; ++ci) {
+                            const int col0 = (half * C::CPT + ci) * 32;
+                            fm_acc_ld<D>(ACC0 + lane_off, col0, X[ci]);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float v = fmaf(X[ci][j], rh_inv * vecs[V_C2S * D + col0 + j], vecs[V_C2B * D + col0 + j]);
+                                X[ci][j] = valid ? fm_act(v, act) : 0.f;
+                            }
+                            if (L.x_out && valid) {
+                                float4 *o4 = reinterpret_cast<float4 *>(L.x_out + grow * D + col0);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o4[i] = make_float4(X[ci][4 * i], X[ci][4 * i + 1], X[ci][4 * i + 2], X[ci][4 * i + 3]);
+                            }
+                            if (L.pool) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sPJ + fm_swz<D>(r, col0 / 4 + i)),
+                                                 "f"(X[ci][4 * i]), "f"(X[ci][4 * i + 1]), "f"(X[ci][4 * i + 2]), "f"(X[ci][4 * i + 3]) : "memory");
+                            }
+                        }
+                        if (L.pool) {
+                            // per-graph readout (global_add_pool_sparse / global_mean_pool_sparse, utils_graph_learning.py:23-41):
+                            // rows of a graph summed in row order -> deterministic
+                            fm_bar_compute();
+                            const int col = ct % D;
+                            for (int g = g0 + ct / D; g < g1; g += FM_COMPUTE_THREADS / D) {
+                                const int ra = (int)(__ldg(P.node_ptr + g) - row0), rb = (int)(__ldg(P.node_ptr + g + 1) - row0);
+                                float acc = 0.f;
+                                for (int rr = ra; rr < rb; ++rr) {
+                                    float t;
+                                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sPJ + fm_swz<D>(rr, col >> 2) + (uint32_t)((col & 3) << 2)));
+                                    acc += t;
+                                }
+                                if (L.pool == 2 && rb > ra) acc /= (float)(rb - ra);
+                                L.pooled[(int64_t)g * D + col] = acc;
+                            }
+                        }
+                        if (l + 1 < nL) rx_inv = write_operand(X);
+                    }
+                }
+                g0 = g1;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*FmEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static FmEncodeTiledFn fm_encode_fn() {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        return (FmEncodeTiledFn)p;
+    return nullptr;
+}
+
+// fp16 [rows, D] row-major, box = [D rows, 64 halves], 128-byte swizzle
+static int fm_make_map(CUtensorMap *map, const void *base, int64_t rows, int D) {
+    FmEncodeTiledFn fn = fm_encode_fn();
+    if (!fn) return GSN_E_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)D};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled (fused model) failed: %d", (int)r);
+        return GSN_E_CUDA;
+    }
+    return GSN_OK;
+}
+
+template <int D>
+static int fm_launch(const CUtensorMap &hi, const CUtensorMap &lo, const FmParams &p, cudaStream_t stream) {
+    constexpr int smem = FmCfg<D>::SMEM;
+    GSN_CUDA_OK(cudaFuncSetAttribute(fused_model_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const unsigned grid = (unsigned)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
+    fused_model_kernel<D><<<grid, 384, smem, stream>>>(hi, lo, p);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("fused_model_kernel");
+    return GSN_OK;
+}
+
+}  // namespace gsn
+
+using namespace gsn;
+
+extern "C" int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream_) {
+    if (!h_m) return GSN_E_INVALID;
+    const GsnFusedModel &m = *h_m;
+    if (m.n_layers < 1 || m.n_layers > GSN_FUSED_MAX_LAYERS || (m.D != 64 && m.D != 128) || m.G < 0 || m.N < 0 ||
+        !m.d_rowptr || !m.d_node_ptr || !m.d_Whi || !m.d_Wlo || !m.d_status || m.graphs_per_unit < 1 || m.n_mats < 2)
+        return GSN_E_INVALID;
+    if (m.N + 1 >= (int64_t)1 << 31 || m.G >= (int64_t)1 << 30) return GSN_E_UNSUPPORTED;
+    if (m.G == 0 || m.N == 0) return GSN_OK;
+    FmParams p;
+    p.n_layers = m.n_layers;
+    p.rowptr = m.d_rowptr; p.nbr = m.d_nbr; p.node_ptr = m.d_node_ptr;
+    p.x0 = m.d_x0; p.x0_ld = m.x0_ld; p.x0_d = m.x0_d;
+    p.G = (int32_t)m.G; p.unit = m.graphs_per_unit; p.n_units = (int32_t)ceil_div(m.G, m.graphs_per_unit);
+    p.status = m.d_status;
+    for (int l = 0; l < m.n_layers; ++l) {
+        const GsnFusedLayer &s = m.layers[l];
+        FmLayer &d = p.layer[l];
+        if (!s.d_vec || s.n_node_cols < 0 || s.n_edge_cols < 0 || (s.n_node_cols > 0 && (!s.d_node_rows || !s.d_Tn)) ||
+            (s.n_edge_cols > 0 && (!s.d_edge_rows || !s.d_Te || s.te_rows < 1)) || (s.d_Tu && !s.d_tu_rows) ||
+            (s.pool && !s.d_pooled) || s.mat0 < 0 || s.mat0 + (s.has_dense ? 5 : 2) > m.n_mats)
+            return GSN_E_INVALID;
+        if (s.has_dense && l == 0 && (!m.d_x0 || m.x0_d < 1 || m.x0_d > m.D)) return GSN_E_INVALID;
+        if (!s.has_dense && l > 0) return GSN_E_UNSUPPORTED;      // a layer after the first always consumes dense rows
+        if (m.E > 0 && !m.d_nbr) return GSN_E_INVALID;
+        d.node_rows = s.d_node_rows; d.Tn = s.d_Tn; d.tu_rows = s.d_tu_rows; d.Tu = s.d_Tu; d.edge_rows = s.d_edge_rows;
+        d.Te = s.d_Te; d.vec = s.d_vec; d.pooled = s.d_pooled; d.x_out = s.d_x_out;
+        d.n_node_cols = s.n_node_cols; d.tu_stride = s.tu_stride; d.n_edge_cols = s.n_edge_cols; d.te_rows = s.te_rows;
+        d.has_dense = s.has_dense ? 1 : 0; d.mat0 = s.mat0; d.act_msg = s.act_msg; d.act_upd = s.act_upd; d.act_out = s.act_out;
+        d.pool = s.pool;
+    }
+    CUtensorMap hi, lo;
+    int rc;
+    if ((rc = fm_make_map(&hi, m.d_Whi, (int64_t)m.n_mats * m.D, m.D))) return rc;
+    if ((rc = fm_make_map(&lo, m.d_Wlo, (int64_t)m.n_mats * m.D, m.D))) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (m.D == 128) return fm_launch<128>(hi, lo, p, stream);
+    return fm_launch<64>(hi, lo, p, stream);
+}

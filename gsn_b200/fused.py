@@ -120,7 +120,7 @@ class FusedForward:
             if s0 is not None:
                 Wxi, Wxj, Wii, Wij, Wq_id, Wq_ef = [None if W is None else W * s0[:, None]
                                                     for W in (Wxi, Wxj, Wii, Wij, Wq_id, Wq_ef)]
-            L = {'dh': dh, 'act_mlp': conv.activation_name, 'x_cat': x_cat and i == 0, 'ef_cat': ef_cat,
+            L = {'dh': dh, 'd_in': d_in, 'act_mlp': conv.activation_name, 'x_cat': x_cat and i == 0, 'ef_cat': ef_cat,
                  'uses_ids': conv.uses_ids, 'uses_ef': conv.uses_ef, 'local': conv.id_scope == 'local', 'flow': conv.flow}
             # node side of the first Linear
             Wp = torch.cat((Wxi, Wxj), 0).contiguous()                  # [2dh, d_in]
@@ -203,23 +203,14 @@ class FusedForward:
                                   pr.fc[1].weight.contiguous(), pr.fc[1].bias.contiguous(), pr.activation_name))
         self._stamp = self._version_stamp()
 
-    # ------------------------------------------------------------------ forward
-    @torch.no_grad()
-    def __call__(self, data, raw_identifiers: Optional[torch.Tensor] = None, vocab: Optional[List[torch.Tensor]] = None):
-        """data: same attribute bag as GNNSubstructures.forward plus `node_ptr` (int64 [G+1]).
-        raw_identifiers/vocab: un-encoded COUNT output and the one_hot_unique vocabulary; when omitted,
-        data.identifiers must hold the encoded ranks (as in the reference)."""
+    # ------------------------------------------------------------------ categorical inputs -> table rows
+    def _context(self, data, raw_identifiers, vocab):
+        """per-call state shared by the layers: dense x (or None), index columns, the concatenated vocabulary"""
         m = self.model
         if m.training:
             raise RuntimeError('FusedForward is inference-only')
         if self._stamp != self._version_stamp():
             self.prepare()
-        dev = data.edge_index.device
-        edge_index = data.edge_index
-        N = data.x.shape[0]
-        E = edge_index.shape[1]
-        node_ptr = data.node_ptr
-
         # identifier rows into the one-hot table of the id encoder (offset inside the table added later)
         ids = raw_identifiers if raw_identifiers is not None else data.identifiers
         id_dims = m.id_encoder[0].encoder.d_in
@@ -233,6 +224,7 @@ class FusedForward:
                 if [int(v.numel()) for v in vocab] != [int(d) for d in id_dims]:
                     raise ValueError('vocabulary sizes differ from the d_in of the model\'s identifier encoder')
                 self._vocab_key, self._vcat = key, torch.cat(vocab)
+                self._vocab_keep = list(vocab)       # pins the tensors whose data_ptr is the cache key
                 self._vptr, o2 = [], 0
                 for v in vocab:
                     self._vptr.append((o2, o2 + v.numel()))
@@ -240,48 +232,64 @@ class FusedForward:
             vcat, vptr = self._vcat, self._vptr
         else:
             vcat, vptr = None, [None] * len(id_dims)
-
-        x = None
         x_cat = _is_onehot(m.input_node_encoder)
         xi = data.x if data.x.dim() == 2 else data.x.unsqueeze(-1)
-        if not x_cat:
-            x = m.input_node_encoder(data.x)
+        x = None if x_cat else m.input_node_encoder(data.x)
+        efi = None
+        if getattr(data, 'edge_features', None) is not None:
+            efi = data.edge_features if data.edge_features.dim() == 2 else data.edge_features.unsqueeze(-1)
+        return {'ids': ids, 'id_off': id_off, 'vcat': vcat, 'vptr': vptr, 'xi': xi, 'x': x, 'efi': efi,
+                'N': data.x.shape[0], 'E': data.edge_index.shape[1], 'dev': data.edge_index.device, 'ef_rows_cache': {}}
+
+    def _layer_rows(self, L, ctx, plan):
+        """(node_rows int32 [N, n_node_cols] | None, edge_rows int32 [E, n_groups] in CSR order | None) of one layer"""
+        ids, vptr, id_off, vcat, dev = ctx['ids'], ctx['vptr'], ctx['id_off'], ctx['vcat'], ctx['dev']
+        node_cols, edge_cols = [], []
+        if L['x_cat']:
+            node_cols.append((ctx['xi'][:, 0], None, 0))
+        if L['uses_ids']:
+            cols = [(ids[:, c], vptr[c], id_off[c]) for c in range(ids.shape[1])]
+            if L['local']:
+                edge_cols += cols
+            else:
+                node_cols += [(s, v, off + L['Tn_off_ids']) for s, v, off in cols]
+        if L['uses_ef'] and L['ef_cat']:
+            edge_cols.append((ctx['efi'][:, 0], None, L['Te_off_ef']))
+        eg = L['edge_groups']
+        if eg is not None:
+            edge_cols = [(s, v, eg['off'][c]) for c, (s, v, _) in enumerate(edge_cols)]
+        node_rows = ops.encode_rows(node_cols, vcat, ctx['N'], dev) if node_cols else None
+        # edge rows are produced directly in CSR order (perm = plan.eid): the message kernel then reads them
+        # sequentially instead of chasing eid -> row
+        only_ef = len(edge_cols) == 1 and L['uses_ef'] and L['ef_cat']
+        key = (L['Te_off_ef'], L['flow'])
+        cache = ctx['ef_rows_cache']
+        if only_ef and key in cache:
+            return node_rows, cache[key]
+        if eg is not None:
+            edge_rows = ops.encode_rows_grouped(edge_cols, eg['group'], eg['mult'], eg['n_groups'], vcat, ctx['E'], dev,
+                                                perm=plan.eid)
+        else:
+            edge_rows = ops.encode_rows(edge_cols, vcat, ctx['E'], dev, perm=plan.eid) if edge_cols else None
+        if only_ef:
+            cache[key] = edge_rows
+        return node_rows, edge_rows
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def __call__(self, data, raw_identifiers: Optional[torch.Tensor] = None, vocab: Optional[List[torch.Tensor]] = None):
+        """data: same attribute bag as GNNSubstructures.forward plus `node_ptr` (int64 [G+1]).
+        raw_identifiers/vocab: un-encoded COUNT output and the one_hot_unique vocabulary; when omitted,
+        data.identifiers must hold the encoded ranks (as in the reference)."""
+        m = self.model
+        ctx = self._context(data, raw_identifiers, vocab)
+        edge_index, N, node_ptr = data.edge_index, ctx['N'], data.node_ptr
+        x = ctx['x']
         x_interm = [x]
-        ef_rows_cache = {}          # (offset) -> encoded edge-feature rows in CSR order, shared by the layers
         for i, (conv, L) in enumerate(zip(m.conv, self.layers)):
             plan = ops.edge_plan(edge_index, N, L['flow'])
             dh = L['dh']
-            # ---- index columns
-            node_cols, edge_cols = [], []
-            if L['x_cat']:
-                node_cols.append((xi[:, 0], None, 0))
-            if L['uses_ids']:
-                cols = [(ids[:, c], vptr[c], id_off[c]) for c in range(ids.shape[1])]
-                if L['local']:
-                    edge_cols += cols
-                else:
-                    node_cols += [(s, v, off + L['Tn_off_ids']) for s, v, off in cols]
-            if L['uses_ef'] and L['ef_cat']:
-                efi = data.edge_features if data.edge_features.dim() == 2 else data.edge_features.unsqueeze(-1)
-                edge_cols.append((efi[:, 0], None, L['Te_off_ef']))
-            eg = L['edge_groups']
-            if eg is not None:
-                edge_cols = [(s, v, eg['off'][c]) for c, (s, v, _) in enumerate(edge_cols)]
-            node_rows = ops.encode_rows(node_cols, vcat, N, dev) if node_cols else None
-            # edge rows are produced directly in CSR order (perm = plan.eid): the message kernel then reads them
-            # sequentially instead of chasing eid -> row
-            only_ef = len(edge_cols) == 1 and L['uses_ef'] and L['ef_cat']
-            key = (L['Te_off_ef'], L['flow'])
-            if only_ef and key in ef_rows_cache:
-                edge_rows = ef_rows_cache[key]
-            else:
-                if eg is not None:
-                    edge_rows = ops.encode_rows_grouped(edge_cols, eg['group'], eg['mult'], eg['n_groups'], vcat, E, dev,
-                                                        perm=plan.eid)
-                else:
-                    edge_rows = ops.encode_rows(edge_cols, vcat, E, dev, perm=plan.eid) if edge_cols else None
-                if only_ef:
-                    ef_rows_cache[key] = edge_rows
+            node_rows, edge_rows = self._layer_rows(L, ctx, plan)
             # ---- dense parts
             P = ops.linear(x, L['Wp'], bias=L['bp']) if L['Wp'] is not None else None
             Q = None
@@ -303,12 +311,17 @@ class FusedForward:
             x = ops.linear(H, L['U2'], bias=L['c2'], scale=L['sm'], shift=L['tm'], activation=self._act_model)
             x_interm.append(x)
 
-        out = None
+        self.last_x_interm = x_interm          # layer outputs of the last call (parity checks of the one-kernel path)
         mean = m.readout == 'mean'
-        for i, pr in enumerate(self.proj):
+        return self._project([None if pr is None else ops.pool_ptr(x_interm[i], node_ptr, mean)
+                              for i, pr in enumerate(self.proj)])
+
+    def _project(self, pooled_list):
+        """sum of the JK projections of the pooled layer outputs (models_graph_classification.py:236-240)"""
+        out = None
+        for pr, pooled in zip(self.proj, pooled_list):
             if pr is None:
                 continue
-            pooled = ops.pool_ptr(x_interm[i], node_ptr, mean)
             if pr[0] == 'linear':
                 out = ops.linear(pooled, pr[1], bias=pr[2], out=out, accumulate=out is not None)
             else:

@@ -52,12 +52,21 @@ class Batch:
 class GSNPipeline:
 
     def __init__(self, model, subgraph_dicts, induced: bool, id_scope: str, encoder: UniqueEncoder,
-                 max_nodes_per_graph: int, fused: bool = True):
-        from . import fused as _fused
+                 max_nodes_per_graph: int, fused=True):
+        """fused: True = best available (one-kernel forward when the model allows it, else the per-layer fused path),
+        'model' / 'layers' force one of the two, False = the drop-in per-layer modules"""
+        from . import fused as _fused, fused_model as _fm
         self.model, self.subgraph_dicts, self.induced, self.id_scope = model, subgraph_dicts, induced, id_scope
         # inference fast path (indices instead of one-hot tensors, BN folded, own GEMM kernels) when the
         # model configuration allows it; otherwise the per-layer path
-        self.fused = _fused.FusedForward(model) if (fused and _fused.supported(model) and not model.training) else None
+        self.fused = None
+        if fused and not model.training:
+            if fused in (True, 'model') and _fm.supported(model, max_nodes_per_graph):
+                self.fused = _fm.FusedModel(model)
+            elif fused == 'model':
+                raise NotImplementedError('one-kernel forward: unsupported model / graph size')
+            elif _fused.supported(model):
+                self.fused = _fused.FusedForward(model)
         self.encoder, self.max_nodes = encoder, int(max_nodes_per_graph)
         self.n_cols = total_columns(subgraph_dicts)
         self._graph: Optional[torch.cuda.CUDAGraph] = None

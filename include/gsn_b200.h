@@ -312,6 +312,48 @@ int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_t *d_eid, c
  * d_perm = d_eid), which removes one dependent load per edge; 0: indexed by edge_index column. */
 
 /* ------------------------------------------------------------------ */
+/* whole-model fused forward                                           */
+/* ------------------------------------------------------------------ */
+/*
+ * GNNSubstructures.forward (models_graph_classification.py:204-247, eval mode, 'general' message kind) for a whole
+ * batch in ONE launch.  A PyG batch is block-diagonal, so a tile of whole graphs (<= 128 nodes) is self-contained:
+ * each CTA carries its tile through every layer (split first Linear of msg_fn, neighbour gather + activation + sum,
+ * update_fn with the second message Linear folded in, model BatchNorm + activation, GSN_edge_sparse.py:111-166,
+ * models_misc.py:52-59) with all activations in shared / tensor memory and writes only the per-graph readout
+ * (utils_graph_learning.py:23-41).  GEMMs: tcgen05, 3 x fp16 with exact power-of-two row scaling (fp32-equivalent).
+ *
+ * All matrices are padded to D x D (D = 64 or 128 >= every hidden width; padding rows / columns are zero):
+ *   d_Whi / d_Wlo  fp16 [n_mats * D, D]: rows scaled per output row by a power of two; layer l owns matrices
+ *                  mat0 .. mat0+4 = Wxj, Wxi, U1x, Wf, U2 (has_dense) or mat0, mat0+1 = Wf, U2 (table-only layer 0)
+ *   d_vec          fp32 [9, D] per layer: cJ, cI, shiftI, cU, cF, cV, cB, c2s, c2b  (inverse weight scales, BatchNorm
+ *                  scale / shift and biases folded per output column; gsn_b200/fused_model.py builds them)
+ *   d_Tn [rows, 2D] node-side table rows (P_i half | P_j half), d_Te [te_rows, D] edge-side rows, d_Tu [rows, D]
+ *   d_node_rows int32 [N, n_node_cols], d_edge_rows int32 [E, n_edge_cols] in CSR order, d_tu_rows int32 (stride tu_stride)
+ *   pool: 0 none, 1 sum, 2 mean -> d_pooled fp32 [G, D];  d_x_out (optional) fp32 [N, D] = the layer's output rows
+ * CSR (d_rowptr, d_nbr) from gsn_csr_build.  Graphs must have <= 128 nodes (GSN_S_GRAPH_TOO_LARGE otherwise) and
+ * edges must stay inside their graph (GSN_S_CROSS_GRAPH_EDGE).  graphs_per_unit: consecutive graphs handed to a CTA
+ * at a time (work granularity; tiles are packed greedily inside a unit).
+ */
+#define GSN_FUSED_MAX_LAYERS 8
+typedef struct GsnFusedLayer {
+    const int32_t *d_node_rows; const float *d_Tn;
+    const int32_t *d_tu_rows; const float *d_Tu;
+    const int32_t *d_edge_rows; const float *d_Te;
+    const float *d_vec; float *d_pooled; float *d_x_out;
+    int32_t n_node_cols, tu_stride, n_edge_cols, te_rows, has_dense, mat0, act_msg, act_upd, act_out, pool;
+} GsnFusedLayer;
+typedef struct GsnFusedModel {
+    GsnFusedLayer layers[GSN_FUSED_MAX_LAYERS];
+    int32_t n_layers, D, n_mats, graphs_per_unit;
+    const void *d_Whi; const void *d_Wlo;
+    const int32_t *d_rowptr; const int32_t *d_nbr; const int64_t *d_node_ptr;
+    const float *d_x0; int32_t x0_ld, x0_d;
+    int64_t N, E, G;
+    int32_t *d_status;
+} GsnFusedModel;
+int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream);
+
+/* ------------------------------------------------------------------ */
 /* DGN consumer of COUNT (directional_gsn/)                            */
 /* ------------------------------------------------------------------ */
 /*
