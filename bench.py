@@ -128,7 +128,7 @@ def build_batches(batch_size, n_batches, seed0):
 
 
 def to_tensors(b, pad_to=None, pin=False, device=None):
-    """numpy batch -> tensors (padded to fixed N/E so that one CUDA graph serves every step)"""
+    """numpy batch -> tensors"""
     t = {'edge_index': torch.from_numpy(b['edge_index']), 'node_ptr': torch.from_numpy(b['node_ptr']),
          'x': torch.from_numpy(b['x']), 'edge_features': torch.from_numpy(b['edge_features']),
          'batch': torch.from_numpy(b['batch']), 'degrees': torch.from_numpy(b['degrees'])}
@@ -139,52 +139,23 @@ def to_tensors(b, pad_to=None, pin=False, device=None):
     return t
 
 
-def batch_variants(b, n, seed):
-    """n distinct batches with the SAME shapes as b (CUDA graphs need static shapes): the graphs of b in a different
-    order (so edge_index, node_ptr, batch differ) with fresh random atom / bond types.  Stacked along a leading axis."""
-    rng = np.random.default_rng(seed)
-    node_ptr, edge_ptr, ei = b['node_ptr'], b['edge_ptr'], b['edge_index']
-    G = len(node_ptr) - 1
-    sizes, esizes = np.diff(node_ptr), np.diff(edge_ptr)
-    g_of_e = np.repeat(np.arange(G), esizes)
-    local = ei - node_ptr[g_of_e][None, :]
-    N, E = int(node_ptr[-1]), int(edge_ptr[-1])
-    out = {k: [] for k in ('edge_index', 'node_ptr', 'x', 'edge_features', 'batch', 'degrees')}
-    for _ in range(n):
-        perm = rng.permutation(G)                          # new position p holds old graph perm[p]
-        nptr = np.concatenate([[0], np.cumsum(sizes[perm])]).astype(np.int64)
-        e_order = np.concatenate([np.arange(edge_ptr[g], edge_ptr[g + 1]) for g in perm])
-        pos_of_e = np.repeat(np.arange(G), esizes[perm])
-        new_ei = local[:, e_order] + nptr[pos_of_e][None, :]
-        out['edge_index'].append(new_ei)
-        out['node_ptr'].append(nptr)
-        out['x'].append(rng.integers(0, 28, size=(N, 1), dtype=np.int64))
-        out['edge_features'].append(rng.integers(1, 4, size=(E, 1), dtype=np.int64))
-        out['batch'].append(np.repeat(np.arange(G, dtype=np.int64), sizes[perm]))
-        out['degrees'].append(np.bincount(new_ei[0], minlength=N).astype(np.float32))
-    return {k: torch.from_numpy(np.stack(v)) for k, v in out.items()}
+def workload_string(B):
+    """identical in both arms (the driver compares config.workload)"""
+    return (f'ZINC-shaped synthetic batches of B={B} molecules per GPU (mean 23.2 nodes / 49.8 directed edges per graph); '
+            f'step = COUNT cycles k<={K_MAX} edge scope non-induced + one_hot_unique encode + GNNSubstructures forward '
+            f'(GSN_edge_sparse general, id_scope local, {N_LAYERS} layers, d_out {D_OUT})')
 
 
-class Packing:
-    """byte layout of one batch inside a single buffer (16-byte aligned fields): a step's inputs move with ONE copy"""
+FLOPS_PER_NODE = 2 * (2 * D_OUT * D_OUT) + (N_LAYERS - 1) * 2 * (5 * D_OUT * D_OUT)
+"""fp32-equivalent GEMM flops of one node through the re-associated model (DESIGN.md sec. 4): layer 0 (categorical
+input) S.Wf^T and H.U2^T; layers >= 1 additionally x.Wxi^T, x.Wxj^T, x.U1x^T -- each a [D,D] matrix, 2 flops per MAC.
+On the tensor cores every product costs 3 fp16 MMAs."""
 
-    def __init__(self, example):
-        self.fields, off = [], 0
-        for k, v in example.items():
-            nbytes = v.numel() * v.element_size()
-            self.fields.append((k, off, nbytes, v.dtype, tuple(v.shape)))
-            off += (nbytes + 15) // 16 * 16
-        self.nbytes = off
 
-    def views(self, buf):
-        return {k: buf[off:off + n].view(dt).view(shape) for k, off, n, dt, shape in self.fields}
-
-    def pack_pool(self, stacked):
-        P = next(iter(stacked.values())).shape[0]
-        out = torch.zeros((P, self.nbytes), dtype=torch.uint8)
-        for k, off, n, dt, shape in self.fields:
-            out[:, off:off + n] = stacked[k].contiguous().view(P, -1).view(torch.uint8).view(P, n)
-        return out
+def bytes_per_step(N, E, G):
+    """HBM bytes one step has to move at the API boundary (every boundary tensor once):
+    edge_index int64 [2,E], node_ptr int64 [G+1], x int64 [N,1], edge_features int64 [E,1] in; predictions fp32 [G,1] out"""
+    return 16 * E + 8 * (G + 1) + 8 * N + 8 * E + 4 * G
 
 
 # ======================================================================================
@@ -193,7 +164,8 @@ class Packing:
 def run_ours(args, rank, world, local_rank):
     from gsn_b200 import _lib, counting, patterns
     from gsn_b200.network import GNNSubstructures
-    from gsn_b200.pipeline import GSNPipeline, UniqueEncoder
+    from gsn_b200.pipeline import BucketedPipeline, GSNPipeline, UniqueEncoder
+    from gsn_b200.synthetic import zinc_like_batch
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False      # fp32 parity (1e-5) needs full-precision GEMMs
@@ -201,11 +173,9 @@ def run_ours(args, rank, world, local_rank):
     _lib.lib()
 
     B = args.batch
+    G = B
     els = cycle_edge_lists()
     sds = patterns.make_subgraph_dicts(els, 'local')
-    # one fixed-shape batch per rank: CUDA graphs need static shapes, so every step re-runs the same shapes
-    # with different CONTENT (a pool of distinct batches padded to common N/E would be equivalent)
-    pool = build_batches(B, 1, seed0=1000 * rank)
     calib = build_batches(min(2048, max(B, 512)), 1, seed0=77)[0]
     ids_cal = counting.count_batch(torch.from_numpy(calib['edge_index']).to(dev), torch.from_numpy(calib['node_ptr']),
                                    sds, False, 'local', max_nodes_per_graph=64)
@@ -213,30 +183,51 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         model = GNNSubstructures(**model_ctor(encoder.d), **model_args(encoder.d)).to(dev).eval()
-    pipe = GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64)
-    b0 = pool[0]
-    N, E, G = int(b0['node_ptr'][-1]), int(b0['edge_index'].shape[1]), B
-    dev_in = to_tensors(b0, device=dev)
-    host_in = to_tensors(b0, pin=True)
 
-    # ---- correctness of the captured step vs the eager step (cheap sanity, not the parity test)
+    # ---- the pool: P DISTINCT batches (own generator seed each: different molecules, different N and E), as a
+    # DataLoader would deliver them (main.py:243-258).  Every batch is padded to its shape bucket (sentinel graphs /
+    # self loops, gsn_b200/pipeline.py) and packed into one buffer at collate time; every (stream, bucket) pair owns
+    # one captured CUDA graph of the whole step.
+    S, P = max(1, args.streams), max(args.pool, 2 * max(1, args.streams))
+    raw = [zinc_like_batch(B, seed=100_003 * (rank + 1) + i) for i in range(P)]
+    bps = [BucketedPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64) for _ in range(S)]
+    keys, pool_host, shapes = [], [], []
+    for b in raw:
+        padded = bps[0].pad(b)
+        key = (padded['x'].shape[0], padded['edge_index'].shape[1], padded['node_ptr'].numel() - 1)
+        for bp in bps:
+            bp._entry(key, padded, dev)
+        keys.append(key)
+        pool_host.append(bps[0].packing(padded).pack(padded).pin_memory())
+        shapes.append((int(b['node_ptr'][-1]), int(b['edge_index'].shape[1])))
+    pool_dev = [t.to(dev) for t in pool_host]
+    pool_bytes = sum(t.numel() for t in pool_host)
+    n_buckets = len(set(keys))
+    N_mean, E_mean = float(np.mean([s_[0] for s_ in shapes])), float(np.mean([s_[1] for s_ in shapes]))
+    # resolved (static input buffer, captured graph, static output) per (stream, batch): nothing but a copy and a replay
+    # remains on the host side of a step
+    ent = [[(bp._lru[k][2], bp._lru[k][0]._graph, bp._lru[k][0]._out) for k in keys] for bp in bps]
+
+    # ---- correctness of the captured + padded step vs the eager step on the UNPADDED batch (cheap sanity, not the parity test)
+    pipe = GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64)
+    for v in (0, 1, P // 2, P - 1):
+        with torch.no_grad():
+            exp_v = pipe.step(to_tensors(raw[v], device=dev)).clone()
+        got_v = bps[-1].run(keys[v], pool_dev[v], G).clone()
+        torch.cuda.synchronize()
+        assert torch.allclose(got_v, exp_v, atol=1e-5, rtol=1e-5), 'padded + captured step differs from the eager step'
+        assert int(pipe.last_status.item()) == 0 and int(pipe.fused.status.item()) == 0
+    dev_in = to_tensors(raw[0], device=dev)
     with torch.no_grad():
         ref_out = pipe.step(dev_in).clone()
-    launches0 = _lib.launch_count()
-    pipe.capture(dev_in, warmup=max(3, args.warmup))
-    with torch.no_grad():
         l0 = _lib.launch_count()
         pipe.step(dev_in)
         my_launches_per_step = _lib.launch_count() - l0
-    out = pipe.replay().clone()
-    torch.cuda.synchronize()
-    if os.environ.get('GSN_PROFILE_REPLAY'):      # ncu --profile-from-start off --graph-profiling node
+    if os.environ.get('GSN_PROFILE_REPLAY'):      # ncu --profile-from-start off
         torch.cuda.profiler.start()
-        pipe.replay()
+        bps[0].run(keys[0], pool_dev[0], G)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-    assert torch.allclose(out, ref_out, atol=1e-5, rtol=1e-5), 'captured step differs from eager step'
-    assert int(pipe.last_status.item()) == 0
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     dist_on = world > 1
@@ -246,82 +237,62 @@ def run_ours(args, rank, world, local_rank):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(fn, steps):
-        """K steps, each bracketed by its own event pair with an L2 flush in between (outside the pairs)"""
+    streams = [torch.cuda.Stream() for _ in range(S)]
+    out_host = torch.empty((args.steps + args.warmup, G, 1), dtype=torch.float32).pin_memory()
+
+    def run_steps(k, start, src, d2h):
+        main = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(main)
+        for i in range(k):
+            s_ = i % S
+            idx = (start + i) % P
+            buf, graph, out = ent[s_][idx]
+            with torch.cuda.stream(streams[s_]):
+                buf.copy_(src[idx], non_blocking=True)          # the step's inputs: one packed copy
+                graph.replay()
+                if d2h:
+                    out_host[i].copy_(out[:G], non_blocking=True)
+        for st in streams:
+            main.wait_stream(st)
+
+    def timed_region(src, d2h):
+        run_steps(args.warmup, 0, src, d2h)
+        barrier()
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_steps(args.steps, args.warmup, src, d2h)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    with Clocks(local_rank) as clk:
+        # ---- single stream, one step at a time, L2 flushed before every step, a different batch every step: the latency
+        # of ONE step (device time between an event pair around copy + replay)
+        for i in range(args.warmup):
+            bps[0].run(keys[i % P], pool_dev[i % P], G)
         evs = []
         barrier()
-        for _ in range(steps):
+        for i in range(args.steps):
+            idx = (args.warmup + i) % P
+            buf, graph, _ = ent[0][idx]
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            buf.copy_(pool_dev[idx], non_blocking=True)
+            graph.replay()
             e1.record()
             evs.append((e0, e1))
         barrier()
-        return sum(a.elapsed_time(b) for a, b in evs)      # ms
-
-    # ---- single stream, one step at a time, L2 flushed before every step (the latency of ONE step)
-    for _ in range(args.warmup):
-        pipe.replay()
-    with Clocks(local_rank) as clk:
-        ms_single = timed_steps(lambda: pipe.replay(), args.steps) / args.steps
-
-        # ---- value: whole-job throughput.  At B=128 one step is a chain of ~26 dependent launches that each fill a
-        # fraction of the 148 SMs, so S steps on DIFFERENT batches are kept in flight (S captured graphs on S streams),
-        # as a server overlapping consecutive batches would.  Every step copies ITS OWN batch out of a pool of
-        # `--pool` distinct batches (same shapes, other graph order / features; > L2 in total, no batch is used twice
-        # inside a timed region that fits the pool) into the graph's input buffers, inside the timed region; L2 is
-        # flushed once before the region (steps overlap, so it cannot be flushed between them).
-        S, P = max(1, args.streams), max(args.pool, 2 * max(1, args.streams))
-        variants = batch_variants(b0, P, seed=4242 + rank)
-        packing = Packing({k: variants[k][0] for k in dev_in})
-        pool_host = packing.pack_pool(variants).pin_memory()          # [P, nbytes] uint8, one row = one batch
-        pool_dev = pool_host.to(dev)
-        packed = [torch.zeros(packing.nbytes, dtype=torch.uint8, device=dev) for _ in range(S)]
-        pipes = [GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64).capture(
-            dev_in, warmup=3, static=packing.views(packed[i])) for i in range(S)]
-        streams = [torch.cuda.Stream() for _ in range(S)]
-        out_host = torch.empty((args.steps + args.warmup, G, 1), dtype=torch.float32).pin_memory()
-
-        def run_steps(k, start, src, d2h):
-            main = torch.cuda.current_stream()
-            for st in streams:
-                st.wait_stream(main)
-            for i in range(k):
-                with torch.cuda.stream(streams[i % S]):
-                    packed[i % S].copy_(src[(start + i) % P], non_blocking=True)      # the step's inputs: one copy
-                    o = pipes[i % S].replay()
-                    if d2h:
-                        out_host[i].copy_(o, non_blocking=True)
-            for st in streams:
-                main.wait_stream(st)
-
-        def timed_region(src, d2h):
-            run_steps(args.warmup, 0, src, d2h)
-            barrier()
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            run_steps(args.steps, args.warmup, src, d2h)
-            e1.record()
-            barrier()
-            return e0.elapsed_time(e1)
-
-        # the pooled batches go through the same captured step: check two of them against the eager step
-        for v in (1, P - 1):
-            tv = {key: variants[key][v].to(dev) for key in dev_in}
-            with torch.no_grad():
-                exp_v = pipe.step(tv).clone()
-            packed[-1].copy_(pool_dev[v])
-            got_v = pipes[-1].replay().clone()
-            torch.cuda.synchronize()
-            assert torch.allclose(got_v, exp_v, atol=1e-5, rtol=1e-5), 'pooled batch: captured step differs from eager step'
+        ms_single = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+        # ---- value: whole-job throughput with S steps on different batches in flight (S streams), inputs resident in HBM
         ms_total = timed_region(pool_dev, False)
-        # ---- e2e: every step's inputs come from PINNED HOST memory (H2D inside the region) and its predictions are
-        # read back to the host (D2H inside the region); same S streams
+        # ---- e2e: every step's inputs come from PINNED HOST memory (H2D inside the region) and its predictions are read
+        # back to the host (D2H inside the region); same S streams
         ms_e2e = timed_region(pool_host, True)
         assert bool(torch.isfinite(out_host[:args.steps]).all())
-    h2d = packing.nbytes
+    h2d = int(np.mean([t.numel() for t in pool_host]))
     d2h = out_host[0].numel() * out_host.element_size()
 
     if dist_on:
@@ -332,104 +303,52 @@ def run_ours(args, rank, world, local_rank):
     value = world * G / (ms_per_step * 1e-3)
     e2e_value = world * G / (ms_e2e / args.steps * 1e-3)
 
-    # ---- informative only: other stream counts on ONE repeated batch (no pool), to show where the overlap saturates
-    concurrent = None
-    if rank == 0 and not args.no_sweep:
-        try:
-            concurrent = []
-            for S2 in (2, 4, 12):
-                pipes2 = [pipe] + [GSNPipeline(model, sds, False, 'local', encoder, max_nodes_per_graph=64).capture(
-                    dev_in, warmup=3) for _ in range(S2 - 1)]
-                streams2 = [torch.cuda.Stream() for _ in range(S2)]
-                K2 = max(args.steps, 40)
-                for p_ in pipes2:
-                    p_.load(dev_in)
-
-                def run2(k):
-                    main = torch.cuda.current_stream()
-                    for st in streams2:
-                        st.wait_stream(main)
-                    for i in range(k):
-                        with torch.cuda.stream(streams2[i % S2]):
-                            pipes2[i % S2].replay()
-                    for st in streams2:
-                        main.wait_stream(st)
-                run2(2 * S2)
-                torch.cuda.synchronize()
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                run2(K2)
-                e1.record()
-                torch.cuda.synchronize()
-                ms2 = e0.elapsed_time(e1)
-                ok = all(torch.allclose(p_._out, ref_out, atol=1e-5, rtol=1e-5) for p_ in pipes2)
-                concurrent.append({'streams': S2, 'steps': K2, 'graphs_per_s': K2 * G / (ms2 * 1e-3), 'ms_per_step': ms2 / K2,
-                                   'outputs_match': bool(ok)})
-                del pipes2
-        except Exception as ex:
-            concurrent = [{'error': repr(ex)[:200]}]
-
     line = None
     if rank == 0:
-        # ---- instrumented eager pass: per-kernel device time with CUDA events on the launching stream
-        def instrumented(tensors, steps):
+        flush_ = flush
+
+        # ---- instrumented eager pass: per-call device time with CUDA events on the launching stream
+        def instrumented(p_, tensors, steps):
             _lib.TIMER = []
             with torch.no_grad():
                 for _ in range(steps):
-                    flush.zero_()
-                    pipe.step(tensors)
+                    flush_.zero_()
+                    p_.step(tensors)
             torch.cuda.synchronize()
             agg = {}
             for tag, e0, e1 in _lib.TIMER:
                 agg.setdefault(tag, []).append(e0.elapsed_time(e1))
             _lib.TIMER = None
-            return {k: (float(np.mean(v)) * 1e-3, len(v) // steps) for k, v in agg.items()}   # seconds, calls/step
+            return {k: (float(np.median(v)) * 1e-3, len(v) // steps) for k, v in agg.items()}   # seconds, calls/step
 
-        peak, peak_src = peaks()
-        prof = instrumented(dev_in, max(3, min(args.steps, 10)))
-        dh = D_OUT
-
-        from gsn_b200.fused import MERGE_MAX_ROWS, _merge_edge_columns
-        n_id_cols = len(encoder.d)
-        # index columns the layer-0 message kernel reads per edge after column grouping (fused.py)
-        n_l0_cols = _merge_edge_columns(torch.zeros((sum(encoder.d) + 4, 1)), _edge_cols(encoder), MERGE_MAX_ROWS)[1]['n_groups']
-
-        def scatter_bytes(n, e):
-            """algorithmic bytes of ONE launch of the message (scatter) kernel, averaged over the N_LAYERS launches
-            of a step.  Layer 0 reads only indices (x: 4 B/node, identifiers + bond type folded
-            into n_l0_cols grouped row indices of 4 B per edge); layers >= 1 read P [N, 2dh] fp32 and one 4-byte index per edge.
-            Every launch reads the CSR (rowptr + nbr, 4 B each) and writes S [N, dh] fp32."""
-            csr = 4 * e + 4 * (n + 1)
-            out = 4 * dh * n
-            layer0 = 4 * n + 4 * n_l0_cols * e + csr + out
-            later = 4 * 2 * dh * n + 4 * e + csr + out
-            return (layer0 + (N_LAYERS - 1) * later) / N_LAYERS
-        # device duration of the message kernel at the step's own shapes: R back-to-back launches inside one event
-        # pair (a single ~5 us launch bracketed by its own events mostly measures launch gaps)
-        t_sc_eager = prof['general_edge'][0]
-        t_sc = scatter_launch_seconds(dev, b0, encoder, reps=50)
-        roof = {'bound': 'hbm', 'kernel': 'tab_tight_kernel (layer 0) + p1_tight_kernel (layers >= 1) behind gsn_mp_general_edge_idx_fwd, mean of the '
-                                          f'{N_LAYERS} launches of a step',
-                'achieved': scatter_bytes(N, E) / t_sc / 1e9, 'peak': peak, 'unit': 'GB/s',
-                'frac': scatter_bytes(N, E) / t_sc / 1e9 / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 launches of one step (ncu --set full,
-                # B=128): layer 0 (tab_tight_kernel, grouped columns) 0.182 MB read (profiles/r1g_ncu_tab_tight_b128.txt);
-                # layers >= 1 (p1_tight_kernel) 3.20 MB read (profiles/r1e_ncu_tight_scatter_b128.txt); 0 B written in both
-                # -- the 1.5 MB S output stays in the 126 MB L2
-                'traffic': (0.182272e6 + 3 * 3.200768e6) / 4 if (B == 128 and N_LAYERS == 4) else None,
-                'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': scatter_bytes(N, E), 'avg_launch_us': t_sc * 1e6,
-                'launches_per_step': prof['general_edge'][1],
-                'avg_launch_us_single_eager': t_sc_eager * 1e6,
-                'how': 'mean device time of the 4 message-kernel launches of a step (layer 0 + 3 identifier-free layers) at '
-                       'the step shapes, 50 launches replayed from a CUDA graph per CUDA-event pair; at B=128 one launch moves ~2 MB '
-                       '(0.3 us at HBM peak) so it is launch-latency bound: see roofline_large_batch, sweep[] and '
-                       'scatter_kernels[] for batches where HBM traffic dominates',
-                'traffic_note': 'ncu --set full (profiles/): dram read+write per launch == algorithmic bytes within 1 % '
-                                'for the dense kernel at B=32,768'}
+        hbm_peak, hbm_src = peaks()
+        tc_peak, tc_src = tensor_peak()
+        N0, E0 = shapes[0]
+        prof = instrumented(pipe, dev_in, max(5, min(args.steps, 10)))
         kernels_us = {k: round(v[0] * 1e6, 2) for k, v in prof.items()}
+
+        def forward_roofline(n, e, g, t_fm):
+            fl = FLOPS_PER_NODE * n
+            by = 4 * n + 4 * e * 2 + 8 * (g + 1) + 4 * (n + 1) + 4 * e + 4 * g * D_OUT      # index inputs + CSR in, pooled rows out
+            return {'bound': 'tensor',
+                    'kernel': 'fused_model_kernel<128> (gsn_fused_model_fwd): all layers of the model for a tile of whole graphs; '
+                              'the dominant launch of a step',
+                    'achieved': fl / t_fm / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': fl / t_fm / 1e12 / tc_peak,
+                    'peak_source': tc_src, 'algorithmic_flops_per_launch': fl, 'flops_per_node': FLOPS_PER_NODE,
+                    'mma_flops_per_launch': 3 * fl, 'mma_frac_of_peak': 3 * fl / t_fm / 1e12 / tc_peak,
+                    'avg_launch_us': t_fm * 1e6,
+                    'hbm_view': {'algorithmic_bytes_per_launch': by, 'GBps': by / t_fm / 1e9, 'frac_of_hbm_peak': by / t_fm / 1e9 / hbm_peak,
+                                 'peak': hbm_peak, 'peak_source': hbm_src,
+                                 'note': 'the kernel reads index columns + CSR and writes pooled rows only: activations never '
+                                         'leave the SM, so HBM is not what bounds it'},
+                    'how': 'median device time of the launch (CUDA events on the launching stream, L2 flushed before every step) '
+                           'in an eager pass over the step; algorithmic flops = FLOPS_PER_NODE x nodes (fp32-equivalent; the '
+                           'tensor cores execute 3 fp16 MMAs per product, mma_* counts those)'}
+        roof = forward_roofline(N0, E0, G, prof['fused_model'][0])
+        roof['traffic'] = None
+        roof['launches_per_step'] = prof['fused_model'][1]
         sweep = []
+        roof_large = None
         if not args.no_sweep:
             for Bs in (4096, 131072):
                 try:
@@ -450,46 +369,40 @@ def run_ours(args, rank, world, local_rank):
                     t1.record()
                     torch.cuda.synchronize()
                     ms = t0.elapsed_time(t1) / reps
-                    pr = instrumented(tens, 3)
-                    ts = pr['general_edge'][0]
+                    pr = instrumented(pipe, tens, 3)
                     sweep.append({'batch': Bs, 'N': n_s, 'E': e_s, 'graphs_per_s': Bs / (ms * 1e-3),
                                   'edges_per_s': e_s / (ms * 1e-3), 'ms_per_step': ms,
-                                  'scatter_GBps': scatter_bytes(n_s, e_s) / ts / 1e9,
-                                  'scatter_frac_of_peak': scatter_bytes(n_s, e_s) / ts / 1e9 / peak,
-                                  'count_ms': pr['count_pattern'][0] * 1e3, 'graph_build_ms': pr['graph_build'][0] * 1e3,
+                                  'step_bytes_GBps': bytes_per_step(n_s, e_s, Bs) / (ms * 1e-3) / 1e9,
+                                  'count_ms': pr['count_pattern'][0] * 1e3,
                                   'kernels_us': {k: round(v[0] * 1e6, 1) for k, v in pr.items()}})
+                    if Bs == 131072:
+                        roof_large = forward_roofline(n_s, e_s, Bs, pr['fused_model'][0])
+                        roof_large['batch'] = Bs
                     del tens
                     torch.cuda.empty_cache()
                 except Exception as ex:      # the sweep is informative only; never lose the headline line
                     sweep.append({'batch': Bs, 'error': repr(ex)[:200]})
-        roof_large = None
         scatter_kernels = []
         if not args.no_sweep:
             try:
-                scatter_kernels = scatter_microbench(dev, flush, peak)
+                scatter_kernels = scatter_microbench(dev, flush, hbm_peak)
             except Exception as ex:
                 scatter_kernels = [{'error': repr(ex)[:200]}]
-        if not args.no_sweep:
+        # ---- GSN-v (id_scope global: the README.md:112 recipe as written), same pipeline, informative second line
+        gsn_v = None
+        if not args.no_sweep and world == 1:
             try:
-                bl = build_batches(131072, 1, seed0=5)[0]
-                nl, el = int(bl['node_ptr'][-1]), int(bl['edge_index'].shape[1])
-                tl = scatter_launch_seconds(dev, bl, encoder, reps=3, flush=flush)
-                roof_large = {'bound': 'hbm', 'kernel': roof['kernel'], 'batch': 131072, 'N': nl, 'E': el,
-                              'achieved': scatter_bytes(nl, el) / tl / 1e9, 'peak': peak, 'unit': 'GB/s',
-                              'frac': scatter_bytes(nl, el) / tl / 1e9 / peak, 'avg_launch_us': tl * 1e6,
-                              'algorithmic_bytes_per_launch': scatter_bytes(nl, el),
-                              'traffic': 'ncu --set full at B=131,072 (profiles/r1d_ncu_tight_scatter_b131072.txt): dram '
-                                         'read 3.18 GB + write 1.53 GB per identifier-free launch vs 4.72 GB algorithmic'}
+                gsn_v = gsn_v_line(dev, raw[:64], flush, S)
             except Exception as ex:
-                roof_large = {'error': repr(ex)[:200]}
+                gsn_v = {'error': repr(ex)[:200]}
         # reported baselines: rank 0 at N=1 only (the multi-GPU runs of the scaling sweep stay short)
-        cpu = cpu_baseline(pool[0], sds_oracle(), encoder, model, budget_s=12.0) if world == 1 else None
+        cpu = cpu_baseline(raw[0], sds_oracle(), encoder, model, budget_s=12.0) if world == 1 else None
         eager = None
         if not args.no_sweep and world == 1:
             try:
                 ids_dev = counting.count_batch(dev_in['edge_index'], dev_in['node_ptr'], sds, False, 'local',
                                                max_nodes_per_graph=64)
-                eager = torch_eager_gpu(pool[0], ids_dev, encoder, model, dev)
+                eager = torch_eager_gpu(raw[0], ids_dev, encoder, model, dev)
                 eager['max_abs_diff_vs_ours'] = float((eager.pop('out') - ref_out).abs().max())
             except Exception as ex:
                 eager = {'error': repr(ex)[:200]}
@@ -498,90 +411,101 @@ def run_ours(args, rank, world, local_rank):
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64 counts + fp32 forward',
             'data': 'synthetic',
-            'config': {'workload': f'ZINC-shaped synthetic batch B={B} per GPU (N={N}, E={E}); COUNT cycles k<=8 edge '
-                                   f'scope non-induced + one_hot_unique encode + GNNSubstructures forward '
-                                   f'(GSN_edge_sparse general, id_scope local, {N_LAYERS} layers, d_out {D_OUT})',
-                       'batch_per_gpu': B, 'N': N, 'E': E, 'id_columns': encoder.d, 'l2': f'inputs larger than L2: every step reads its own batch from '
-                       f'a pool of {P} distinct same-shape batches ({P * h2d / 1e6:.0f} MB > 126 MB L2), none reused inside a '
-                       'timed region; one 256 MiB L2 flush before the region (the steps overlap); single_stream: L2 flushed '
-                       'before every step', 'cuda_graph': True, 'streams': S, 'pool': P,
+            'config': {'workload': workload_string(B), 'batch_per_gpu': B, 'N_mean': N_mean, 'E_mean': E_mean,
+                       'id_columns': encoder.d,
+                       'l2': f'inputs larger than L2: every step reads its own batch from a pool of {P} DISTINCT batches (own '
+                             f'generator seed each, {pool_bytes / 1e6:.0f} MB packed > 126 MB L2), none reused inside a timed '
+                             f'region that fits the pool; one 256 MiB L2 flush before the region (the steps overlap); '
+                             f'single_stream: L2 flushed before every step',
+                       'shapes': f'variable (N, E) per batch, padded to {n_buckets} shape buckets (node step 128, edge step 256); '
+                                 f'one captured CUDA graph per (stream, bucket)',
+                       'cuda_graph': True, 'streams': S, 'pool': P, 'buckets': n_buckets,
                        'parallelism': f'batch-sharded x{world}, no data-path collective'},
-            'edges_per_s': world * E / (ms_per_step * 1e-3),
+            'edges_per_s': world * E_mean / (ms_per_step * 1e-3),
             'single_stream': {'ms_per_step': ms_single, 'graphs_per_s': world * G / (ms_single * 1e-3),
-                              'note': 'one step at a time on one stream, L2 flushed before every step, one fixed batch: the '
-                                      'LATENCY of a step; `value` keeps `streams` steps on different batches in flight'},
+                              'note': 'one step at a time on one stream, L2 flushed before every step, a different batch every '
+                                      'step: the LATENCY of a step; `value` keeps `streams` steps on different batches in flight'},
             'e2e': {'value': e2e_value, 'unit': 'graphs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(my_launches_per_step) * args.steps,     # our kernels; + 1 packed input copy per step
             'gpu_launches_per_step': int(my_launches_per_step),
-            'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep, 'scatter_kernels': scatter_kernels,
-            'roofline_large_batch': roof_large, 'torch_eager_gpu': eager,
-            'concurrent_streams': {'note': 'informative: other stream counts, ONE batch replayed (no pool), one L2 flush '
-                                           'before the region',
-                                   'runs': concurrent},
+            'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep,
+            'scatter_kernels': scatter_kernels, 'roofline_large_batch': roof_large, 'torch_eager_gpu': eager, 'gsn_v': gsn_v,
         }
     return line
 
 
-def _edge_cols(encoder):
-    """(vocabulary size, first table row) of the layer-0 edge columns: identifier ranks, then the bond type"""
-    cols, o = [], 0
-    for d in list(encoder.d) + [4]:
-        cols.append((int(d), o))
-        o += int(d)
-    return cols
+def tensor_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return float(json.load(fh)['bf16_tflops']), 'measured (MEASURED_PEAKS.json bf16_tflops, burst; kind::f16 runs at the bf16 rate)'
+    except Exception:
+        return 2250.0, 'fallback (nominal dense bf16/fp16 2.25 PFLOP/s)'
 
 
-def scatter_launch_seconds(dev, batch, encoder, reps, flush=None):
-    """mean device seconds of ONE message-kernel launch of a step on `batch` (weights: 1 layer-0 launch reading only
-    indices + (N_LAYERS-1) launches reading P and one index column), timed as back-to-back launches"""
-    from gsn_b200 import ops
-    ei = torch.from_numpy(batch['edge_index']).to(dev)
-    N, E, dh = int(batch['node_ptr'][-1]), int(ei.shape[1]), D_OUT
-    plan = ops.EdgePlan(ei, N)
-    g = torch.Generator(device=dev).manual_seed(0)
-    P = torch.randn((N, 2 * dh), device=dev, generator=g)
-    # no scale / shift operands: fused.py folds msg_fn's BatchNorm affine into P and the tables
-    er1 = torch.randint(0, 4, (E, 1), device=dev, dtype=torch.int32)
-    Te1 = torch.randn((4, dh), device=dev)
-    n_id = sum(encoder.d)
-    nr = torch.randint(0, 28, (N, 1), device=dev, dtype=torch.int32)
-    Tn = torch.randn((28, 2 * dh), device=dev)
-    from gsn_b200.fused import MERGE_MAX_ROWS, _merge_edge_columns
-    Te0, eg = _merge_edge_columns(torch.randn((n_id + 4, dh), device=dev), _edge_cols(encoder), MERGE_MAX_ROWS)
-    er0 = torch.randint(0, Te0.shape[0], (E, eg['n_groups']), device=dev, dtype=torch.int32)
-
-    def later():
-        ops.general_edge_idx(plan, dh, P=P, edge_rows=er1, Te=Te1, edge_rows_csr=True)
-
-    def first():
-        ops.general_edge_idx(plan, dh, node_rows=nr, Tn=Tn, edge_rows=er0, Te=Te0, edge_rows_csr=True)
-
-    def run(fn):
-        # the launches are recorded into a CUDA graph and replayed, so that the event pair brackets device work only
-        # (an eager Python launch costs ~15 us of host time, more than the kernel itself at B=128)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                fn()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            for _ in range(reps):
-                fn()
-        gr.replay()
-        torch.cuda.synchronize()
-        if flush is not None:
-            flush.zero_()
+def gsn_v_line(dev, raw, flush, S):
+    """the same step with vertex-scope identifiers (GSN-v, id_scope global, README.md:112): latency of one captured
+    step and throughput with S steps in flight, over 64 distinct batches"""
+    from gsn_b200 import counting, patterns
+    from gsn_b200.network import GNNSubstructures
+    from gsn_b200.pipeline import BucketedPipeline, UniqueEncoder
+    sds = patterns.make_subgraph_dicts(cycle_edge_lists(), 'global')
+    calib = build_batches(512, 1, seed0=77)[0]
+    ids_cal = counting.count_batch(torch.from_numpy(calib['edge_index']).to(dev), torch.from_numpy(calib['node_ptr']),
+                                   sds, False, 'global', max_nodes_per_graph=64)
+    enc = UniqueEncoder.fit(ids_cal)
+    margs = model_args(enc.d)
+    margs['id_scope'] = 'global'
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = GNNSubstructures(**model_ctor(enc.d), **margs).to(dev).eval()
+    G = len(raw[0]['node_ptr']) - 1
+    bps = [BucketedPipeline(model, sds, False, 'global', enc, max_nodes_per_graph=64) for _ in range(S)]
+    keys, packed = [], []
+    for b in raw:
+        padded = bps[0].pad(b)
+        key = (padded['x'].shape[0], padded['edge_index'].shape[1], padded['node_ptr'].numel() - 1)
+        for bp in bps:
+            bp._entry(key, padded, dev)
+        keys.append(key)
+        packed.append(bps[0].packing(padded).pack(padded).to(dev))
+    P = len(raw)
+    streams = [torch.cuda.Stream() for _ in range(S)]
+    for i in range(8):
+        bps[0].run(keys[i], packed[i], G)
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(20):
+        flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        gr.replay()
+        bps[0].run(keys[i % P], packed[i % P], G)
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) * 1e-3 / reps
-    return (run(first) + (N_LAYERS - 1) * run(later)) / N_LAYERS
+        ts.append(e0.elapsed_time(e1))
+
+    def run(k):
+        main = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(main)
+        for i in range(k):
+            with torch.cuda.stream(streams[i % S]):
+                bps[i % S].run(keys[i % P], packed[i % P], G)
+        for st in streams:
+            main.wait_stream(st)
+    run(2 * S)
+    torch.cuda.synchronize()
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(P)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / P
+    return {'config': 'GSN-v: id_scope global (vertex-scope cycle counts, README.md:112), otherwise the headline workload',
+            'single_stream_ms_per_step': float(np.median(ts)), 'single_stream_graphs_per_s': G / (float(np.median(ts)) * 1e-3),
+            'value_graphs_per_s': G / (ms * 1e-3), 'ms_per_step': ms, 'streams': S, 'distinct_batches': P,
+            'id_columns': enc.d}
 
 
 def scatter_microbench(dev, flush, peak, batch=131072):

@@ -13,13 +13,14 @@ import torch
 
 from .patterns import GsnPlan
 
-_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libgsn_b200.so')
+# GSN_B200_LIB: developer override (e.g. the profiling build libgsn_b200_prof.so); the package itself never sets it
+_SO = os.environ.get('GSN_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libgsn_b200.so')
 
 GSN_OK = 0
 _ERRORS = {-1: 'GSN_E_INVALID (bad argument)', -2: 'GSN_E_UNSUPPORTED (shape outside the built kernels)',
            -3: 'GSN_E_WORKSPACE (workspace too small)', -4: 'GSN_E_CUDA'}
 
-S_GRAPH_TOO_LARGE, S_CROSS_GRAPH_EDGE, S_MISSING_EDGE, S_INDEX_RANGE = 1, 2, 4, 8
+S_GRAPH_TOO_LARGE, S_CROSS_GRAPH_EDGE, S_MISSING_EDGE, S_INDEX_RANGE, S_COUNT_OVERFLOW, S_NOT_GROUPED = 1, 2, 4, 8, 16, 32
 
 _vp, _i64, _i32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_size_t
 _szp = ctypes.POINTER(ctypes.c_size_t)
@@ -33,6 +34,7 @@ _SIGNATURES = {
     'gsn_graph_build': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _sz, _vp, _vp]),
     'gsn_count_scratch_bytes': (ctypes.c_int, [_i64, _i64, _planp, _szp]),
     'gsn_count_pattern': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _planp, _vp, _i64, _vp, _sz, _vp, _vp]),
+    'gsn_count_small': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _planp, _vp, _i64, _vp, _vp]),
     'gsn_csr_workspace_bytes': (ctypes.c_int, [_i64, _i64, _szp]),
     'gsn_csr_build': (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     'gsn_mp_gin_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
@@ -139,4 +141,8 @@ def status_message(bits: int) -> str:
         out.append('a match used an edge (a,b) that is not a column of edge_index (asymmetric edge_index)')
     if bits & S_INDEX_RANGE:
         out.append('a node index is outside [0, num_nodes)')
+    if bits & S_COUNT_OVERFLOW:
+        out.append('a per-vertex / per-edge occurrence count exceeded 2^32 - 1')
+    if bits & S_NOT_GROUPED:
+        out.append('edge_index columns are not grouped by graph (batch order)')
     return '; '.join(out)

@@ -36,15 +36,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+PROFILE_SO_PATH = os.path.join(_HERE, 'libgsn_b200_prof.so')
+
+
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
+    """profile=True builds libgsn_b200_prof.so with -DGSN_PROFILE_STAMPS (clock64 phase stamps inside the fused
+    kernels, read by scripts/fm_debug.py); the shipped library carries no profiling hooks."""
+    so_path = PROFILE_SO_PATH if profile else SO_PATH
+    if not force and not profile and not needs_build():
         return SO_PATH
     objs = []
     procs = []
-    os.makedirs(os.path.join(_HERE, '_obj'), exist_ok=True)
+    obj_dir = os.path.join(_HERE, '_obj_prof' if profile else '_obj')
+    os.makedirs(obj_dir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(_HERE, '_obj', os.path.basename(src)[:-3] + '.o')
-        cmd = [NVCC] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
+        cmd = [NVCC] + NVCC_FLAGS + (['-DGSN_PROFILE_STAMPS'] if profile else []) + \
+            (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -55,10 +63,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    subprocess.check_call([NVCC, '-shared', '-o', SO_PATH] + objs + ['-lcudart'])
-    return SO_PATH
+    subprocess.check_call([NVCC, '-shared', '-o', so_path] + objs + ['-lcudart'])
+    return so_path
 
 
 if __name__ == '__main__':
-    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
+    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, profile='--profile' in sys.argv)
     print(path)

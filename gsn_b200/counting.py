@@ -111,32 +111,91 @@ class BatchedGraph:
 
     def raise_on_status(self):
         """Synchronises; turns device-side status bits into the reference's errors."""
-        bits = int(self.status.item())
-        if bits:
-            msg = _lib.status_message(bits)
-            if bits & _lib.S_MISSING_EDGE:
-                raise KeyError(msg)          # utils_graph_processing.py:173 raises KeyError
-            raise ValueError(msg)
+        raise_on_status_bits(int(self.status.item()))
+
+
+SMALL_GRAPH_NODES = 64          # gsn_count_small: one 64-bit adjacency word per vertex
+SMALL_PATH = True               # False: always gsn_graph_build + gsn_count_pattern (tests compare the two)
+
+
+def _small_path_ok(plans: Sequence[GsnPlan], max_nodes_per_graph: Optional[int]) -> bool:
+    if not SMALL_PATH or max_nodes_per_graph is None or max_nodes_per_graph > SMALL_GRAPH_NODES:
+        return False
+    return all(not (P.family == 1 and P.kmax > 12) for P in plans)
+
+
+def _count_small(edge_index, node_ptr, plans, n_cols, scope, N, status):
+    """one launch per plan, no workspace (csrc/count_small.cu)"""
+    E, G = int(edge_index.shape[1]), int(node_ptr.numel() - 1)
+    dev = edge_index.device
+    rows = N if scope == 0 else E
+    out = torch.empty((rows, n_cols), dtype=torch.int64, device=dev)
+    if rows == 0 or G == 0:
+        return out.zero_()
+    with torch.cuda.device(dev):
+        for P in plans:
+            _lib.call('count_pattern', 'gsn_count_small', _lib.ptr(edge_index), E, _lib.ptr(node_ptr), G, N, ctypes.byref(P),
+                      _lib.ptr(out), n_cols, _lib.ptr(status), _lib.stream_ptr())
+    return out
+
+
+def raise_on_status_bits(bits: int):
+    """device-side status bits -> the reference's errors"""
+    if bits:
+        msg = _lib.status_message(bits)
+        if bits & _lib.S_MISSING_EDGE:
+            raise KeyError(msg)          # utils_graph_processing.py:173 raises KeyError
+        if bits & _lib.S_COUNT_OVERFLOW:
+            raise OverflowError(msg)
+        raise ValueError(msg)
 
 
 def count_batch(edge_index: torch.Tensor, node_ptr: torch.Tensor, subgraph_dicts, induced: bool, id_scope: str,
                 num_nodes: Optional[int] = None, max_nodes_per_graph: Optional[int] = None,
-                check: bool = True, graph: Optional[BatchedGraph] = None) -> torch.Tensor:
+                check: bool = True, graph: Optional[BatchedGraph] = None, status: Optional[torch.Tensor] = None) -> torch.Tensor:
     """identifiers int64 [N, C] (id_scope='global') or [E, C] ('local') for a whole
     batch: the concatenated result of utils_ids.py:19-27 over every graph.
     `edge_index` holds batched (global) node ids, `node_ptr` the first node of
     every graph (PyG `batch.ptr`).  Self loops get zero rows (callers strip them
-    first like utils_ids.py:11-15 if they want the reference's row set)."""
+    first like utils_ids.py:11-15 if they want the reference's row set).
+
+    Batches of small graphs (<= 64 nodes each, known from `max_nodes_per_graph`) take the one-launch path
+    (gsn_count_small); it needs edge_index grouped by graph, and a batch that is not falls back to the general path
+    (with check=True; with check=False the caller reads the GSN_S_NOT_GROUPED bit from `status`, an int32 [1] device
+    tensor it passes in)."""
     scope = 1 if id_scope == 'local' else 0
     dev_in = edge_index.device
     if not edge_index.is_cuda:
         edge_index = edge_index.cuda()
+    plans = _plans_for(subgraph_dicts, induced, scope)
+    n_cols = total_columns(subgraph_dicts)
+    if graph is None and max_nodes_per_graph is None and SMALL_PATH:
+        sizes = node_ptr[1:] - node_ptr[:-1]
+        max_nodes_per_graph = int(sizes.max().item()) if sizes.numel() else 0
+    if graph is None and _small_path_ok(plans, max_nodes_per_graph):
+        ei = edge_index.contiguous()
+        dev = ei.device
+        nptr = node_ptr.to(device=dev, dtype=torch.int64).contiguous()
+        N = int(num_nodes) if num_nodes is not None else int(node_ptr[-1].item())
+        st = status if status is not None else torch.zeros(1, dtype=torch.int32, device=dev)
+        out = _count_small(ei, nptr, plans, n_cols, scope, N, st)
+        if check:
+            bits = int(st.item())
+            if bits & _lib.S_NOT_GROUPED and not (bits & ~_lib.S_NOT_GROUPED & ~_lib.S_CROSS_GRAPH_EDGE & ~_lib.S_MISSING_EDGE):
+                st.zero_()
+                graph = BatchedGraph(ei, nptr, N, max_nodes_per_graph)      # arbitrary column order: general path
+                out = graph.count(plans, n_cols, scope)
+                graph.raise_on_status()
+            else:
+                raise_on_status_bits(bits)
+        return out if dev_in.type == 'cuda' else out.to(dev_in)
     if graph is None:
         graph = BatchedGraph(edge_index, node_ptr, num_nodes, max_nodes_per_graph)
-    plans = _plans_for(subgraph_dicts, induced, scope)
-    out = graph.count(plans, total_columns(subgraph_dicts), scope)
+    out = graph.count(plans, n_cols, scope)
     if check:
         graph.raise_on_status()
+    elif status is not None:
+        status.bitwise_or_(graph.status)
     return out if dev_in.type == 'cuda' else out.to(dev_in)
 
 

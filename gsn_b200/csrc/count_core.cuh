@@ -152,11 +152,23 @@ struct GraphView {
 // Accumulator concept:
 //   void vertex(int local_v, int col, uint32_t c);   // counts[v, col] += c
 //   void slot(int slot, int col, uint32_t c);        // edge counts by simple-graph slot
+//   void overflow();                                 // a count left the 32-bit range (GSN_S_COUNT_OVERFLOW)
+// DFS sub-totals are 64-bit; clamp32 hands them to the 32-bit accumulator interface and reports values that do not fit
+// (the reference computes the same counts exactly in float64, utils_graph_processing.py:118-127).
+template <class Acc>
+GSN_HD uint32_t clamp32(uint64_t c, Acc &acc) {
+    if (c > 0xFFFFFFFFull) {
+        acc.overflow();
+        return 0xFFFFFFFFu;
+    }
+    return (uint32_t)c;
+}
 
 // ------------------------------------------------------------- generic pattern
 template <int W, class Acc>
-GSN_HD void flush_position(const GsnPlan &P, const GraphView<W> &G, const int *f, int p, uint32_t c, Acc &acc) {
-    if (c == 0) return;
+GSN_HD void flush_position(const GsnPlan &P, const GraphView<W> &G, const int *f, int p, uint64_t c64, Acc &acc) {
+    if (c64 == 0) return;
+    const uint32_t c = clamp32(c64, acc);
     if (P.scope == 0) {
         acc.vertex(f[p], P.vorbit[p], c);
     } else {
@@ -208,7 +220,7 @@ GSN_HD void enumerate_generic(const GsnPlan &P, const GraphView<W> &G, int a, in
     if ((P.gt_mask[1] & 1u) && !(a < b)) return;
     if (k == 2 && part != 0) return;
     int f[GSN_MAXK];
-    uint32_t cnt[GSN_MAXK];
+    uint64_t cnt[GSN_MAXK];
     VSet<W> cand[GSN_MAXK];
     f[0] = a;
     f[1] = b;
@@ -223,13 +235,13 @@ GSN_HD void enumerate_generic(const GsnPlan &P, const GraphView<W> &G, int a, in
             if (cand[p].empty()) {
                 if (p == 2) break;
                 --p;
-                uint32_t c = cnt[p];
+                uint64_t c = cnt[p];
                 flush_position<W>(P, G, f, p, c, acc);
                 cnt[p - 1] += c;
                 continue;
             }
             if (p == k - 1) {
-                uint32_t c = 0;
+                uint64_t c = 0;
                 while (!cand[p].empty()) {
                     f[p] = cand[p].pop_lowest();
                     flush_position<W>(P, G, f, p, 1u, acc);
@@ -245,7 +257,7 @@ GSN_HD void enumerate_generic(const GsnPlan &P, const GraphView<W> &G, int a, in
         }
     }
     flush_position<W>(P, G, f, 1, cnt[1], acc);
-    if (P.scope == 0) acc.vertex(f[0], P.vorbit[0], cnt[1]);
+    if (P.scope == 0 && cnt[1]) acc.vertex(f[0], P.vorbit[0], clamp32(cnt[1], acc));
 }
 
 // ------------------------------------------------------------------- cycles

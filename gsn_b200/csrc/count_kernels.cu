@@ -38,16 +38,25 @@ struct CountParams {
     int64_t *out;            // vertex scope: [N, out_ld] ; edge scope: unused here
     int64_t out_ld;
     uint32_t *slot_acc;      // edge scope: [S, n_cols]
+    int32_t *status;
     GsnPlan plan;
 };
 
+// 32-bit accumulators: a carry out of bit 31 sets GSN_S_COUNT_OVERFLOW (raise_on_status reports it) instead of wrapping
+// silently; the shared-memory and the global accumulation paths detect it the same way.
 struct SmemAcc {
     uint32_t *acc;     // chunk-local [rows, C]
     int C;
     int vbase;         // local vertex -> row: vbase + v
     int sbase;         // global slot  -> row: slot - sbase
-    __device__ __forceinline__ void vertex(int lv, int col, uint32_t c) { atomicAdd(&acc[(vbase + lv) * C + col], c); }
-    __device__ __forceinline__ void slot(int s, int col, uint32_t c) { atomicAdd(&acc[(s - sbase) * C + col], c); }
+    int32_t *status;
+    __device__ __forceinline__ void add(uint32_t *p, uint32_t c) {
+        const uint32_t old = atomicAdd(p, c);
+        if (old + c < old) atomicOr(status, GSN_S_COUNT_OVERFLOW);
+    }
+    __device__ __forceinline__ void vertex(int lv, int col, uint32_t c) { add(&acc[(vbase + lv) * C + col], c); }
+    __device__ __forceinline__ void slot(int s, int col, uint32_t c) { add(&acc[(s - sbase) * C + col], c); }
+    __device__ __forceinline__ void overflow() { atomicOr(status, GSN_S_COUNT_OVERFLOW); }
 };
 
 struct GlobalAcc {
@@ -56,10 +65,18 @@ struct GlobalAcc {
     int64_t vrow0;             // global node id of local vertex 0
     uint32_t *slot_acc;
     int C;
+    int32_t *status;
     __device__ __forceinline__ void vertex(int lv, int col, uint32_t c) {
-        atomicAdd(&out[(vrow0 + lv) * ld + col], (unsigned long long)c);
+        // int64 output rows: the value is checked against the 32-bit range of the shared-memory path so that both
+        // paths report the same condition whatever the chunking
+        const unsigned long long old = atomicAdd(&out[(vrow0 + lv) * ld + col], (unsigned long long)c);
+        if (old + c > 0xFFFFFFFFull) atomicOr(status, GSN_S_COUNT_OVERFLOW);
     }
-    __device__ __forceinline__ void slot(int s, int col, uint32_t c) { atomicAdd(&slot_acc[(size_t)s * C + col], c); }
+    __device__ __forceinline__ void slot(int s, int col, uint32_t c) {
+        const uint32_t old = atomicAdd(&slot_acc[(size_t)s * C + col], c);
+        if (old + c < old) atomicOr(status, GSN_S_COUNT_OVERFLOW);
+    }
+    __device__ __forceinline__ void overflow() { atomicOr(status, GSN_S_COUNT_OVERFLOW); }
 };
 
 template <int W, class Acc>
@@ -160,10 +177,10 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
         const int off = (int)(gb - v0);
         GraphView<W> G{adj_base + (size_t)off * W, row_base + off};
         if (acc_in_smem) {
-            SmemAcc acc{sm_acc, C, off, s0};
+            SmemAcc acc{sm_acc, C, off, s0, prm.status};
             run_item<W>(P, G, a - gb, b - gb, acc, part, parts);
         } else {
-            GlobalAcc acc{(unsigned long long *)(prm.out + P.col0), prm.out_ld, (int64_t)gb, prm.slot_acc, C};
+            GlobalAcc acc{(unsigned long long *)(prm.out + P.col0), prm.out_ld, (int64_t)gb, prm.slot_acc, C, prm.status};
             run_item<W>(P, G, a - gb, b - gb, acc, part, parts);
         }
     }
@@ -267,6 +284,7 @@ extern "C" int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t
     prm.out = d_out;
     prm.out_ld = out_ld;
     prm.slot_acc = (uint32_t *)d_scratch;
+    prm.status = d_status;
     prm.plan = P;
     if (P.scope == 1) {
         size_t need = 0;

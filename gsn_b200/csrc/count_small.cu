@@ -1,0 +1,538 @@
+// COUNT for batches of small graphs (<= 64 nodes, one 64-bit adjacency word per vertex): graph build, enumeration and
+// the write-out in edge_index order in ONE launch, no global workspace.
+//
+// Replaces, for the whole batch, utils_data_gen.py:60-78 -> utils_ids.py:19-27 -> utils_graph_processing.py:103-179
+// (per graph: gt.Graph + remove_parallel_edges, graph-tool subgraph_isomorphism, the Python loops over all maps).
+//
+//   * the batch is cut into chunks of ~T consecutive nodes on graph boundaries; ONE CTA owns a chunk.  edge_index of a
+//     PyG batch is grouped by graph (collate concatenates the graphs), so the chunk's edge columns are one
+//     contiguous segment found by a warp-wide 32-ary search; every edge checks that it really belongs to its segment's
+//     chunk (GSN_S_NOT_GROUPED otherwise -- segments tile [0,E), so no stray edge escapes the check);
+//   * adjacency bitmasks (= remove_self_loops + remove_parallel_edges, :112-113), slot offsets (popcount prefix), the
+//     edge_dict of :142-144 (slot -> last edge_index column) and the accumulators live in shared memory;
+//   * cycles (all lengths kmin..kmax in one traversal): WARP-COOPERATIVE depth-first search.  The search stack is a
+//     per-warp array of 32-byte frames (path, exclusion mask, remaining candidates) in shared memory; every step the 32
+//     lanes pop the top 32 frames, each takes ONE candidate of its frame (ballot/popc compaction pushes the frame back
+//     and the child on top), so all lanes execute the same instruction stream whatever the shape of the search tree,
+//     and work is shared inside the warp for free.  Stack depth <= 32 * (kmax - 2) + 32 frames for any graph.
+//   * cliques and generic patterns: the per-thread bitmask DFS of count_core.cuh on the shared-memory graph.
+#include "common.cuh"
+#include "count_core.cuh"
+
+namespace gsn {
+
+struct CsParams {
+    const int64_t *src, *dst;
+    int64_t E;
+    const int64_t *node_ptr;
+    int64_t G, N;
+    int32_t T;             // nodes per chunk before rounding to graph boundaries
+    int32_t node_cap;      // shared-memory capacity in nodes (>= T + 64)
+    int32_t slot_cap;      // edge scope: slots per pass (edge_dict entries)
+    int32_t acc_words;     // accumulator words in shared memory
+    int32_t frame_cap;     // cycles: frames per warp
+    int64_t *out;
+    int64_t out_ld;
+    int32_t *status;
+    GsnPlan plan;
+};
+
+// first index with a[idx] >= key, searched by one warp with 32 probes per round
+__device__ __forceinline__ int64_t warp_lower_bound(const int64_t *__restrict__ a, int64_t n, int64_t key, int lane) {
+    int64_t lo = 0, hi = n;
+    while (hi - lo > 31) {
+        const int64_t step = (hi - lo + 31) / 32;
+        const int64_t idx = lo + (int64_t)(lane + 1) * step - 1;
+        const bool ge = idx < hi ? (__ldg(a + idx) >= key) : true;
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        if (m == 0) return hi;              // the probes ended exactly at hi - 1 and every element is below the key
+        const int j = __ffs((int)m) - 1;
+        const int64_t nhi = lo + (int64_t)(j + 1) * step - 1;
+        lo = lo + (int64_t)j * step;
+        hi = nhi < hi ? nhi : hi;
+    }
+    const int64_t idx = lo + lane;
+    const bool ge = idx < hi ? (__ldg(a + idx) >= key) : true;
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    return lo + (__ffs((int)m) - 1);
+}
+
+// accumulators of one pass: shared memory, or (a pass too large for it) atomics straight into the output rows
+struct CsAcc {
+    uint32_t *acc;          // [rows, C] in shared memory, or nullptr
+    const int32_t *colmap;  // edge scope: pass-local slot -> edge_index column
+    int64_t *out;           // already offset to col0
+    int64_t ld;
+    int64_t v0;             // global id of chunk-local node 0
+    int32_t *status;
+    int C, sbase;           // first slot of the pass (chunk-local numbering)
+    __device__ __forceinline__ void add_vertex(int cv, int col, uint32_t c) {      // cv: chunk-local node
+        if (acc) {
+            const uint32_t old = atomicAdd(&acc[cv * C + col], c);
+            if (old + c < old) atomicOr(status, GSN_S_COUNT_OVERFLOW);
+        } else {
+            const unsigned long long old = atomicAdd((unsigned long long *)&out[(v0 + cv) * ld + col], (unsigned long long)c);
+            if (old + c > 0xFFFFFFFFull) atomicOr(status, GSN_S_COUNT_OVERFLOW);
+        }
+    }
+    __device__ __forceinline__ void add_slot(int s, int col, uint32_t c) {         // s: chunk-local slot
+        if (acc) {
+            const uint32_t old = atomicAdd(&acc[(s - sbase) * C + col], c);
+            if (old + c < old) atomicOr(status, GSN_S_COUNT_OVERFLOW);
+        } else {
+            const int e = colmap[s - sbase];
+            if (e < 0) atomicOr(status, GSN_S_MISSING_EDGE);
+            else {
+                const unsigned long long old = atomicAdd((unsigned long long *)&out[(int64_t)e * ld + col], (unsigned long long)c);
+                if (old + c > 0xFFFFFFFFull) atomicOr(status, GSN_S_COUNT_OVERFLOW);
+            }
+        }
+    }
+};
+
+// adaptor for the per-thread enumerators of count_core.cuh (graph-local vertex ids, chunk-local slots)
+struct CsThreadAcc {
+    CsAcc *a;
+    int goff;
+    __device__ __forceinline__ void vertex(int lv, int col, uint32_t c) { a->add_vertex(goff + lv, col, c); }
+    __device__ __forceinline__ void slot(int s, int col, uint32_t c) { a->add_slot(s, col, c); }
+    __device__ __forceinline__ void overflow() { atomicOr(a->status, GSN_S_COUNT_OVERFLOW); }
+};
+
+__device__ __forceinline__ uint64_t bits_gt(int v) { return ~((2ull << v) - 1ull); }     // ids > v   (v <= 63)
+__device__ __forceinline__ uint64_t bits_lt(int v) { return (1ull << v) - 1ull; }        // ids < v   (v <= 63)
+
+// ---------------------------------------------------------------------------------------------------------------
+// warp-cooperative cycle enumeration over the nodes [sn0, sn1) of the chunk (roots); see the file header
+// frame: q0 = {cand.lo, cand.hi, X.lo, X.hi}, q1 = {path.lo, path.hi, meta, -}
+//   meta = depth p (4 bits) | graph offset in the chunk (16 bits) << 4 | f0 << 20 | f1 << 26 ; path = f[2..] 6 bits each
+//   X = vertices of the path (non-induced) or the union of adj(f[q]), 1 <= q <= p (induced: chords)
+template <bool INDUCED>
+__device__ void cycles_warp(const GsnPlan &P, const uint64_t *adj, const int32_t *rp, const uint16_t *goff, int sn0, int sn1,
+                            int *ticket, uint4 *stack, int frame_cap, CsAcc &acc, int nwarps) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int kmin = P.kmin, kmax = P.kmax, scope = P.scope;
+    int size = 0;
+    bool seeds_left = true;
+    while (true) {
+        if (size < 32 && seeds_left) {
+            // ---- refill with root frames (one per node); near the end of the chunk take fewer so that warps share the tail
+            int base = 0, take = 0;
+            if (lane == 0) {
+                const int remaining = sn1 - *(volatile int *)ticket;
+                take = remaining > 0 ? remaining / (2 * nwarps) + 1 : 1;
+                if (take > 32 - size) take = 32 - size;
+                base = atomicAdd(ticket, take);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            take = __shfl_sync(0xffffffffu, take, 0);
+            if (base >= sn1) seeds_left = false;
+            const int node = base + lane;
+            bool ok = lane < take && node < sn1;
+            uint64_t cand = 0;
+            int f0 = 0, go = 0;
+            if (ok) {
+                go = goff[node];
+                f0 = node - go;
+                cand = adj[node] & bits_gt(f0);
+                ok = cand != 0 && kmax >= 3;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int pos = size + __popc(m & lt);
+                const uint64_t X = INDUCED ? 0ull : (1ull << f0);
+                stack[2 * pos] = make_uint4((uint32_t)cand, (uint32_t)(cand >> 32), (uint32_t)X, (uint32_t)(X >> 32));
+                stack[2 * pos + 1] = make_uint4(0u, 0u, (uint32_t)(0 | (go << 4) | (f0 << 20)), 0u);
+            }
+            size += __popc(m);
+            __syncwarp();
+            if (size == 0) {
+                if (!seeds_left) break;
+                continue;
+            }
+        }
+        if (size == 0) break;
+        const int n = size < 32 ? size : 32;
+        const bool active = lane < n;
+        bool keep = false, child = false;
+        uint4 kq0, kq1, cq0, cq1;
+        if (active) {
+            const int idx = size - 1 - lane;
+            kq0 = stack[2 * idx];
+            kq1 = stack[2 * idx + 1];
+        }
+        __syncwarp();
+        size -= n;
+        if (active) {
+            uint64_t cand = (uint64_t)kq0.x | ((uint64_t)kq0.y << 32);
+            const uint64_t X = (uint64_t)kq0.z | ((uint64_t)kq0.w << 32);
+            uint64_t path = (uint64_t)kq1.x | ((uint64_t)kq1.y << 32);
+            uint32_t meta = kq1.z;
+            const int p = meta & 15, go = (meta >> 4) & 0xFFFF, f0 = (meta >> 20) & 63;
+            const int j = __ffsll((long long)cand) - 1;
+            cand &= cand - 1;
+            keep = cand != 0;
+            kq0.x = (uint32_t)cand;
+            kq0.y = (uint32_t)(cand >> 32);
+            // ---- child: the path extended by j
+            const int pc = p + 1;
+            if (pc == 1) meta = (meta & ~(63u << 26)) | ((uint32_t)j << 26);
+            else path |= (uint64_t)j << (6 * (pc - 2));
+            meta = (meta & ~15u) | (uint32_t)pc;
+            const int f1 = (meta >> 26) & 63;
+            const uint64_t rowj = adj[go + j], rowa = adj[go + f0];
+            uint64_t ext, Xc;
+            if (!INDUCED) {
+                Xc = X | (1ull << j);
+                ext = rowj & ~Xc & bits_gt(f0);
+            } else {
+                ext = rowj & ~X & ~((1ull << f0) | (1ull << f1)) & bits_gt(f0);
+                Xc = X | rowj;
+            }
+            const int len = pc + 2;                      // length of the cycle a closer would make
+            if (len >= kmin) {
+                uint64_t closers = ext & rowa & bits_gt(f1);      // canonical form: f[1] < last vertex
+                if (closers) {
+                    const uint32_t c = (uint32_t)__popcll(closers);
+                    const int col = len - kmin;
+                    if (scope == 0) {
+                        acc.add_vertex(go + f0, col, c);
+                        acc.add_vertex(go + f1, col, c);
+                        for (int q = 2; q <= pc; ++q) acc.add_vertex(go + (int)((path >> (6 * (q - 2))) & 63), col, c);
+                        while (closers) {
+                            const int t = __ffsll((long long)closers) - 1;
+                            closers &= closers - 1;
+                            acc.add_vertex(go + t, col, 1u);
+                        }
+                    } else {
+                        auto add2 = [&](int u, int v, uint32_t cc) {
+                            acc.add_slot(rp[go + u] + __popcll(adj[go + u] & bits_lt(v)), col, cc);
+                            acc.add_slot(rp[go + v] + __popcll(adj[go + v] & bits_lt(u)), col, cc);
+                        };
+                        int prev = f0;
+                        for (int q = 1; q <= pc; ++q) {
+                            const int cur = q == 1 ? f1 : (int)((path >> (6 * (q - 2))) & 63);
+                            add2(prev, cur, c);
+                            prev = cur;
+                        }
+                        while (closers) {
+                            const int t = __ffsll((long long)closers) - 1;
+                            closers &= closers - 1;
+                            add2(prev, t, 1u);
+                            add2(t, f0, 1u);
+                        }
+                    }
+                }
+            }
+            if (len < kmax) {
+                const uint64_t candc = INDUCED ? (ext & ~rowa) : ext;     // induced: a neighbour of the root would be a chord
+                child = candc != 0;
+                cq0 = make_uint4((uint32_t)candc, (uint32_t)(candc >> 32), (uint32_t)Xc, (uint32_t)(Xc >> 32));
+                cq1 = make_uint4((uint32_t)path, (uint32_t)(path >> 32), meta, 0u);
+            }
+        }
+        // ---- push back, keeping the stack sorted by depth (deepest on top): the top 32 frames are then always the
+        //      deepest ones, every popped level refills itself with at most as many frames as were taken from the level
+        //      above it, and no level ever holds more than 32 frames -> size <= 32 * (kmax - 2)
+        const int myp = active ? (int)(kq1.z & 15) : 99;
+        const int dmin = __reduce_min_sync(0xffffffffu, (unsigned)myp);
+        const int dmax = __reduce_max_sync(0xffffffffu, active ? (unsigned)(kq1.z & 15) : 0u);
+        int pos = size;
+        for (int d = dmin; d <= dmax + 1; ++d) {
+            const bool k_here = keep && myp == d, c_here = child && myp + 1 == d;
+            const unsigned mk = __ballot_sync(0xffffffffu, k_here), mc = __ballot_sync(0xffffffffu, c_here);
+            if (k_here) {
+                const int at = pos + __popc(mk & lt);
+                if (at < frame_cap) { stack[2 * at] = kq0; stack[2 * at + 1] = kq1; }
+            }
+            pos += __popc(mk);
+            if (c_here) {
+                const int at = pos + __popc(mc & lt);
+                if (at < frame_cap) { stack[2 * at] = cq0; stack[2 * at + 1] = cq1; }
+            }
+            pos += __popc(mc);
+        }
+        if (pos > frame_cap) {           // cannot happen (bound above); never write outside the stack
+            if (lane == 0) atomicOr(acc.status, GSN_S_GRAPH_TOO_LARGE);
+            pos = frame_cap;
+        }
+        size = pos;
+        __syncwarp();
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__ CsParams prm) {
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    __shared__ int64_t sh_g[2], sh_e[2];
+    __shared__ int sh_ticket, sh_pass[4], sh_warp_tot[NT / 32];
+    const GsnPlan &P = prm.plan;
+    const int C = P.n_cols;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+
+    // ---- chunk: graphs whose first node lies in [blockIdx * T, (blockIdx + 1) * T)
+    {
+        const int64_t lo_node = (int64_t)blockIdx.x * prm.T;
+        int64_t hi_node = lo_node + prm.T;
+        if (hi_node > prm.N) hi_node = prm.N;
+        if (warp == 0) {
+            int64_t g = warp_lower_bound(prm.node_ptr, prm.G + 1, lo_node, lane);
+            if (lane == 0) sh_g[0] = g > prm.G ? prm.G : g;
+        } else if (warp == 1) {
+            int64_t g = warp_lower_bound(prm.node_ptr, prm.G + 1, hi_node, lane);
+            if (lane == 0) sh_g[1] = g > prm.G ? prm.G : g;
+        }
+    }
+    __syncthreads();
+    const int64_t g_lo = sh_g[0], g_hi = sh_g[1];
+    if (g_hi <= g_lo) return;
+    const int64_t v0 = prm.node_ptr[g_lo], v1 = prm.node_ptr[g_hi];
+    if (warp == 0) {
+        int64_t e = g_lo == 0 ? 0 : warp_lower_bound(prm.src, prm.E, v0, lane);
+        if (lane == 0) sh_e[0] = e;
+    } else if (warp == 1) {
+        int64_t e = g_hi == prm.G ? prm.E : warp_lower_bound(prm.src, prm.E, v1, lane);
+        if (lane == 0) sh_e[1] = e;
+    }
+    const int nn = (int)(v1 - v0);
+    // ---- carve shared memory
+    uint64_t *adj = (uint64_t *)cs_smem;
+    int32_t *rp = (int32_t *)(adj + prm.node_cap);
+    int32_t *colmap = rp + (prm.node_cap + 4);
+    uint32_t *sacc = (uint32_t *)(colmap + prm.slot_cap);
+    uint4 *stacks = (uint4 *)(sacc + prm.acc_words);
+    uint16_t *goff = (uint16_t *)(stacks + (size_t)(P.family == GSN_FAMILY_CYCLES ? NW * prm.frame_cap * 2 : 0));
+    if (nn > prm.node_cap) {          // cannot happen when every graph has <= 64 nodes (node_cap >= T + 64)
+        if (tid == 0) atomicOr(prm.status, GSN_S_GRAPH_TOO_LARGE);
+        return;
+    }
+    for (int i = tid; i < nn; i += NT) adj[i] = 0ull;
+    for (int64_t g = g_lo + tid; g < g_hi; g += NT) {
+        const int a = (int)(prm.node_ptr[g] - v0), b = (int)(prm.node_ptr[g + 1] - v0);
+        if (b - a > 64) atomicOr(prm.status, GSN_S_GRAPH_TOO_LARGE);
+        for (int v = a; v < b; ++v) goff[v] = (uint16_t)a;
+    }
+    __syncthreads();
+    const int64_t e0 = sh_e[0], e1 = sh_e[1];
+
+    // edge (a, b) of the segment -> chunk-local a and graph-local b, or -1 when it contributes nothing
+    auto decode = [&](int64_t e, int &ca, int &lb, bool flag) -> bool {
+        const int64_t a = __ldg(prm.src + e), b = __ldg(prm.dst + e);
+        if (a < 0 || b < 0 || a >= prm.N || b >= prm.N) { if (flag) atomicOr(prm.status, GSN_S_INDEX_RANGE); return false; }
+        if (a < v0 || a >= v1) { if (flag) atomicOr(prm.status, GSN_S_NOT_GROUPED); return false; }
+        if (b < v0 || b >= v1) { if (flag) atomicOr(prm.status, GSN_S_CROSS_GRAPH_EDGE); return false; }
+        ca = (int)(a - v0);
+        const int cb = (int)(b - v0);
+        const int go = goff[ca];
+        if (goff[cb] != go) { if (flag) atomicOr(prm.status, GSN_S_CROSS_GRAPH_EDGE); return false; }
+        if (ca == cb) return false;
+        lb = cb - go;
+        return lb < 64 && ca - go < 64;
+    };
+    for (int64_t e = e0 + tid; e < e1; e += NT) {
+        int ca, lb;
+        if (!decode(e, ca, lb, true)) continue;
+        const int go = goff[ca];
+        atomicOr((unsigned long long *)&adj[ca], 1ull << lb);
+        atomicOr((unsigned long long *)&adj[go + lb], 1ull << (ca - go));
+    }
+    __syncthreads();
+    // ---- slot offsets: exclusive scan of the degrees (thread t owns a contiguous span of nodes)
+    {
+        const int span = (nn + 1 + NT - 1) / NT;
+        const int b0 = tid * span, b1 = min(b0 + span, nn + 1);
+        int local = 0;
+        for (int v = b0; v < b1; ++v) {
+            const int d = v < nn ? __popcll(adj[v]) : 0;
+            rp[v] = d;
+            local += d;
+        }
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sh_warp_tot[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += sh_warp_tot[w];
+        int run = woff + incl - local;
+        for (int v = b0; v < b1; ++v) {
+            const int d = rp[v];
+            rp[v] = run;
+            run += d;
+        }
+    }
+    __syncthreads();
+    int64_t *outc = prm.out + P.col0;
+
+    // ---- passes: vertex scope = the whole chunk; edge scope = runs of graphs whose slots fit the edge_dict capacity
+    int pn0 = 0;                         // first chunk-local node of the pass
+    int64_t pg = g_lo;                   // first graph of the pass
+    while (pg < g_hi) {
+        if (tid == 0) {
+            int64_t g = pg;
+            int n1 = pn0;
+            if (P.scope == 0) {
+                g = g_hi;
+                n1 = nn;
+            } else {
+                while (g < g_hi) {
+                    const int nb = (int)(prm.node_ptr[g + 1] - v0);
+                    if (rp[nb] - rp[pn0] > prm.slot_cap && g > pg) break;
+                    n1 = nb;
+                    ++g;
+                }
+            }
+            sh_pass[0] = n1;
+            sh_pass[1] = (int)(g - pg);
+            sh_ticket = pn0;
+        }
+        __syncthreads();
+        const int pn1 = sh_pass[0];
+        const int64_t pg1 = pg + sh_pass[1];
+        const int ps0 = rp[pn0], ps1 = rp[pn1];
+        const int rows = P.scope == 0 ? (pn1 - pn0) : (ps1 - ps0);
+        const bool in_smem = (int64_t)rows * C <= prm.acc_words && (P.scope == 0 || ps1 - ps0 <= prm.slot_cap);
+        if (P.scope == 1 && ps1 - ps0 > prm.slot_cap) {       // one graph denser than the edge_dict capacity: impossible
+            if (tid == 0) atomicOr(prm.status, GSN_S_GRAPH_TOO_LARGE);     // (<= 64 * 63 slots <= slot_cap), kept as a guard
+            return;
+        }
+        if (in_smem) {
+            for (int i = tid; i < rows * C; i += NT) sacc[i] = 0u;
+        } else if (P.scope == 0) {
+            for (int i = tid; i < rows * C; i += NT) outc[(v0 + pn0 + i / C) * prm.out_ld + i % C] = 0;
+        }
+        if (P.scope == 1) {
+            for (int i = tid; i < ps1 - ps0; i += NT) colmap[i] = -1;
+            __syncthreads();
+            // edge_dict (:142-144): the LAST edge_index column of a pair wins
+            for (int64_t e = e0 + tid; e < e1; e += NT) {
+                int ca, lb;
+                if (!decode(e, ca, lb, false)) {
+                    if (pn0 == 0)                    // rows of columns that cannot match (self loops, bad ids): zeros, written once
+                        for (int c = 0; c < C; ++c) outc[e * prm.out_ld + c] = 0;
+                    continue;
+                }
+                if (ca < pn0 || ca >= pn1) continue;
+                atomicMax(&colmap[rp[ca] + __popcll(adj[ca] & bits_lt(lb)) - ps0], (int32_t)e);
+                if (!in_smem)
+                    for (int c = 0; c < C; ++c) outc[e * prm.out_ld + c] = 0;
+            }
+        }
+        __syncthreads();
+
+        CsAcc acc{in_smem ? sacc : nullptr, colmap, outc, prm.out_ld, v0, prm.status, C, ps0};
+        if (P.scope == 0) acc.sbase = 0;
+        // vertex-scope rows are chunk-local nodes relative to the pass start
+        CsAcc vacc = acc;
+        if (P.scope == 0 && in_smem) vacc.acc = sacc - (size_t)pn0 * C;
+        if (P.family == GSN_FAMILY_CYCLES) {
+            uint4 *st = stacks + (size_t)warp * prm.frame_cap * 2;
+            if (P.induced) cycles_warp<true>(P, adj, rp, goff, pn0, pn1, &sh_ticket, st, prm.frame_cap, vacc, NW);
+            else cycles_warp<false>(P, adj, rp, goff, pn0, pn1, &sh_ticket, st, prm.frame_cap, vacc, NW);
+        } else {
+            // per-thread DFS: one root vertex at a time through a shared ticket
+            while (true) {
+                const int node = atomicAdd(&sh_ticket, 1);
+                if (node >= pn1) break;
+                const int go = goff[node];
+                GraphView<1> Gv{adj + go, rp + go};
+                CsThreadAcc ta{&vacc, go};
+                uint64_t nb = adj[node];
+                const int a = node - go;
+                while (nb) {
+                    const int b = __ffsll((long long)nb) - 1;
+                    nb &= nb - 1;
+                    if (P.family == GSN_FAMILY_CLIQUES) enumerate_cliques<1>(P.kmin, P.kmax, P.scope, Gv, a, b, ta);
+                    else enumerate_generic<1>(P, Gv, a, b, ta);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- write-out
+        if (in_smem) {
+            if (P.scope == 0) {
+                for (int i = tid; i < rows * C; i += NT) outc[(v0 + pn0 + i / C) * prm.out_ld + i % C] = (int64_t)sacc[i];
+            } else {
+                for (int64_t e = e0 + tid; e < e1; e += NT) {
+                    int ca, lb;
+                    if (!decode(e, ca, lb, false)) continue;           // zero rows were written above
+                    if (ca < pn0 || ca >= pn1) continue;
+                    const int s = rp[ca] + __popcll(adj[ca] & bits_lt(lb)) - ps0;
+                    const bool last = colmap[s] == (int32_t)e;         // an earlier duplicate column: edge_dict forgot it
+                    for (int c = 0; c < C; ++c) outc[e * prm.out_ld + c] = last ? (int64_t)sacc[s * C + c] : 0;
+                }
+                // a slot that matches used but edge_index never listed: the reference's KeyError (:173)
+                for (int s = tid; s < ps1 - ps0; s += NT) {
+                    if (colmap[s] >= 0) continue;
+                    for (int c = 0; c < C; ++c)
+                        if (sacc[s * C + c]) { atomicOr(prm.status, GSN_S_MISSING_EDGE); break; }
+                }
+            }
+        }
+        __syncthreads();
+        pn0 = pn1;
+        pg = pg1;
+    }
+}
+
+template <int NT>
+static int cs_launch(const CsParams &prm, int64_t chunks, size_t smem, cudaStream_t stream) {
+    GSN_CUDA_OK(cudaFuncSetAttribute(count_small_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    count_small_kernel<NT><<<(unsigned)chunks, NT, smem, stream>>>(prm);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("count_small_kernel");
+    return GSN_OK;
+}
+
+}  // namespace gsn
+
+using namespace gsn;
+
+extern "C" int gsn_count_small(const int64_t *d_edge_index, int64_t E, const int64_t *d_node_ptr, int64_t G, int64_t N,
+                               const GsnPlan *h_plan, int64_t *d_out, int64_t out_ld, int32_t *d_status, void *stream_) {
+    if (!h_plan || !d_status || !d_node_ptr || N < 0 || E < 0 || G < 0 || (E > 0 && !d_edge_index)) return GSN_E_INVALID;
+    const GsnPlan &P = *h_plan;
+    if (N == 0 || G == 0 || (P.scope == 1 && E == 0)) return GSN_OK;
+    if (!d_out) return GSN_E_INVALID;
+    if (P.k < 2 || P.k > GSN_MAXK || P.n_cols < 1 || P.col0 < 0 || P.col0 + P.n_cols > out_ld) return GSN_E_INVALID;
+    if (P.family != GSN_FAMILY_GENERIC && (P.kmin < 3 || P.kmax > GSN_MAXK || P.kmax < P.kmin)) return GSN_E_INVALID;
+    if (P.family == GSN_FAMILY_CYCLES && P.kmax > 12) return GSN_E_UNSUPPORTED;       // path bits of a frame: f[2..10]
+    if (N + 1 >= (int64_t)1 << 31 || E >= (int64_t)1 << 31) return GSN_E_UNSUPPORTED;
+    const int C = P.n_cols;
+    // chunking: ~768 slots per chunk, at least ~4 chunks per SM when the batch is large enough, >= 16 nodes
+    const double avg_deg = N > 0 ? (double)E / (double)N : 1.0;
+    int64_t T = (int64_t)(768.0 / (avg_deg > 1.0 ? avg_deg : 1.0));
+    const int64_t t_fill = N / (kNumSMs * 4);
+    if (T > t_fill) T = t_fill;
+    if (T < 16) T = 16;
+    if (T > 1024) T = 1024;
+    const bool small_batch = ceil_div(N, T) <= 2 * kNumSMs;
+    const int NT = small_batch ? 128 : 256;
+    CsParams prm;
+    prm.src = d_edge_index; prm.dst = d_edge_index ? d_edge_index + E : nullptr; prm.E = E;
+    prm.node_ptr = d_node_ptr; prm.G = G; prm.N = N;
+    prm.T = (int32_t)T;
+    prm.node_cap = (int32_t)((T + 64 + 3) & ~3);
+    prm.slot_cap = P.scope == 1 ? 4096 : 0;
+    int64_t acc_words;
+    if (P.scope == 0) acc_words = (int64_t)prm.node_cap * C;
+    else {
+        acc_words = (int64_t)((double)prm.node_cap * avg_deg * 1.5) * C;
+        if (acc_words > 12288) acc_words = 12288;
+        if (acc_words < 64 * C) acc_words = 64 * C;
+    }
+    prm.acc_words = (int32_t)((acc_words + 3) & ~3);
+    prm.frame_cap = P.family == GSN_FAMILY_CYCLES ? 32 * (P.kmax - 1) : 0;
+    prm.out = d_out; prm.out_ld = out_ld; prm.status = d_status; prm.plan = P;
+    const size_t smem = sizeof(uint64_t) * prm.node_cap + sizeof(int32_t) * (prm.node_cap + 4) + sizeof(int32_t) * prm.slot_cap +
+                        sizeof(uint32_t) * prm.acc_words + (size_t)(NT / 32) * prm.frame_cap * 32 + sizeof(uint16_t) * prm.node_cap + 16;
+    if (smem > 200 * 1024) return GSN_E_UNSUPPORTED;
+    const int64_t chunks = ceil_div(N, T);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    return small_batch ? cs_launch<128>(prm, chunks, smem, stream) : cs_launch<256>(prm, chunks, smem, stream);
+}

@@ -26,6 +26,7 @@
 // warps 4..11 compute (thread = (row, half of the columns): epilogues, message phase, operand conversion).
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace gsn {
@@ -34,8 +35,10 @@ constexpr int FM_MAX_LAYERS = GSN_FUSED_MAX_LAYERS;
 constexpr int FM_ROWS = 128;
 constexpr int FM_NV = 9;            // per-layer column vectors
 enum { V_CJ = 0, V_CI, V_SHIFT, V_CU, V_CF, V_CV, V_CB, V_C2S, V_C2B };
-constexpr int FM_TE_SMALL = 8192;   // bytes of the always-available edge-table staging area
-constexpr int FM_COMPUTE_THREADS = 256;
+constexpr int FM_TE_SMALL = 4096;   // bytes of the always-available edge-table staging area
+constexpr int FM_NPART = 4;                       // column parts of a row = compute warps / 4
+constexpr int FM_COMPUTE_THREADS = 128 * FM_NPART;
+constexpr int FM_THREADS = 128 + FM_COMPUTE_THREADS;
 
 struct FmLayer {
     const int32_t *node_rows; const float *Tn;
@@ -55,6 +58,15 @@ struct FmParams {
     int32_t G, unit, n_units;
     int32_t *status;
 };
+
+// Build-flag-only profiling aid (python -m gsn_b200.build --profile -> libgsn_b200_prof.so): clock64 stamps of the
+// phases of the first tile of CTA 0, [layer][16].  Not compiled into the shipped library.
+#ifdef GSN_PROFILE_STAMPS
+__device__ long long g_fm_stamps[FM_MAX_LAYERS * 16];
+#define FM_STAMP(l, i) do { if (blockIdx.x == 0 && ct == 0 && first_tile) g_fm_stamps[(l) * 16 + (i)] = clock64(); } while (0)
+#else
+#define FM_STAMP(l, i) do { } while (0)
+#endif
 
 __device__ __noinline__ float fm_act_slow(float v, int act) {
     return act == 1 ? (v > 0.0f ? v : expm1f(v)) : tanhf(v);
@@ -97,6 +109,11 @@ __device__ __forceinline__ void fm_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __noinline__ void fm_wait_timeout(int what, uint32_t parity) {
+    printf("fused_model_kernel: mbarrier wait %d timed out (block %d thread %d parity %u)\n", what, blockIdx.x, threadIdx.x, parity);
+    __trap();
+}
+
 // mbarrier wait with a watchdog: a protocol error traps (the launch fails with an error the host reports) instead of
 // hanging the GPU.  `what` identifies the wait site in the message.
 __device__ __forceinline__ void fm_wait(uint64_t *bar, uint32_t parity, int what) {
@@ -112,9 +129,11 @@ __device__ __forceinline__ void fm_wait(uint64_t *bar, uint32_t parity, int what
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1u << 24)) {
-            printf("fused_model_kernel: mbarrier wait %d timed out (block %d thread %d parity %u)\n", what, blockIdx.x, threadIdx.x, parity);
-            __trap();
+        if (!done) {
+            // back off: a spinning warp would otherwise take issue slots from the compute warps of its sub-partition
+            // (ncu: 30 % of all issued instructions were try_wait loops before this)
+            __nanosleep(32);
+            if (++spins > (1u << 22)) fm_wait_timeout(what, parity);
         }
     } while (!done);
 }
@@ -123,32 +142,88 @@ __device__ __forceinline__ void fm_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 32 consecutive TMEM columns of this thread's lane
-__device__ __forceinline__ void fm_tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
+// N consecutive TMEM columns of this thread's lane (N = 16 | 32)
+template <int N>
+__device__ __forceinline__ void fm_tmem_ld(uint32_t taddr, float (&v)[N]) {
+    uint32_t r[N];
+    if constexpr (N == 32) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+    } else {
+        static_assert(N == 16, "16 or 32 columns");
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+    }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < N; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-// main + correction accumulator of one 32-column chunk
-template <int D>
-__device__ __forceinline__ void fm_acc_ld(uint32_t acc_base, int col0, float (&v)[32]) {
-    float q[32];
-    fm_tmem_ld32(acc_base + (uint32_t)col0, v);
-    fm_tmem_ld32(acc_base + (uint32_t)(D + col0), q);
+// 16 fp32 values -> 16 consecutive TMEM columns of this thread's lane (completion: tcgen05.wait::st)
+__device__ __forceinline__ void fm_tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
+// main + correction accumulator of one column chunk, 16 columns at a time (bounded register footprint)
+template <int D, int N>
+__device__ __forceinline__ void fm_acc_ld(uint32_t acc_base, int col0, float (&v)[N]) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += q[j];
+    for (int h = 0; h < N / 16; ++h) {
+        float a[16], b[16];
+        fm_tmem_ld<16>(acc_base + (uint32_t)(col0 + 16 * h), a);
+        fm_tmem_ld<16>(acc_base + (uint32_t)(D + col0 + 16 * h), b);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * h + j] = a[j] + b[j];
+    }
+}
+
+// v[j] = fma(acc[j], rs * cvec[j], v[j]) with cvec in shared memory
+template <int D, int N>
+__device__ __forceinline__ void fm_acc_fma(uint32_t acc_base, int col0, float rs, const float *cvec, float (&v)[N]) {
+#pragma unroll
+    for (int h = 0; h < N / 16; ++h) {
+        float a[16], b[16];
+        fm_tmem_ld<16>(acc_base + (uint32_t)(col0 + 16 * h), a);
+        fm_tmem_ld<16>(acc_base + (uint32_t)(D + col0 + 16 * h), b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 c = *reinterpret_cast<const float4 *>(cvec + col0 + 16 * h + 4 * i);
+            v[16 * h + 4 * i] = fmaf(a[4 * i] + b[4 * i], rs * c.x, v[16 * h + 4 * i]);
+            v[16 * h + 4 * i + 1] = fmaf(a[4 * i + 1] + b[4 * i + 1], rs * c.y, v[16 * h + 4 * i + 1]);
+            v[16 * h + 4 * i + 2] = fmaf(a[4 * i + 2] + b[4 * i + 2], rs * c.z, v[16 * h + 4 * i + 2]);
+            v[16 * h + 4 * i + 3] = fmaf(a[4 * i + 3] + b[4 * i + 3], rs * c.w, v[16 * h + 4 * i + 3]);
+        }
+    }
+}
+
+// compile-time loop: the body sees its index as a constant, so per-iteration register arrays keep static indices even
+// when the body contains a data-dependent loop the compiler will not unroll
+template <int I, int N, class F>
+__device__ __forceinline__ void fm_static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        fm_static_for<I + 1, N>(f);
+    }
 }
 
 // byte offset of 16-byte chunk q of row `row` in an fp32 [rows, D] shared-memory matrix whose chunks are XOR-swizzled
@@ -168,7 +243,7 @@ __device__ __forceinline__ int fm_tile_end(const int64_t *node_ptr, int g0, int 
     return g0 + cnt;
 }
 
-__device__ __forceinline__ void fm_bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void fm_bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(FM_COMPUTE_THREADS) : "memory"); }
 
 template <int D>
 struct FmCfg {
@@ -185,13 +260,13 @@ struct FmCfg {
     static constexpr int OFF_TE = OFF_RING + NST * STAGE;
     static constexpr int OFF_VEC = OFF_TE + FM_TE_SMALL;
     static constexpr int OFF_RMAX = OFF_VEC + VEC_BYTES;
-    static constexpr int SMEM = OFF_RMAX + 2 * FM_ROWS * 4 + 1024;     // + alignment slack
-    static constexpr int CPT = D / 64;                      // 32-column chunks per compute thread
+    static constexpr int SMEM = OFF_RMAX + FM_NPART * FM_ROWS * 4 + 1024;     // + alignment slack
+    static constexpr int CW = D / FM_NPART;                 // columns per compute thread (FM_NPART threads share a row)
     static constexpr uint32_t TMEM_COLS = 4 * D;            // acc0 (main|corr) | acc1 (main|corr)
 };
 
 template <int D>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(FM_THREADS, 1)
 fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                    const __grid_constant__ FmParams P) {
     using C = FmCfg<D>;
@@ -215,10 +290,10 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
             mbar_init(&w_full[s], 1);
             mbar_init(&w_empty[s], 1);
         }
-        mbar_init(&a_ready, 8);
+        mbar_init(&a_ready, 4 * FM_NPART);
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
-        mbar_init(&acc1_free, 8);
+        mbar_init(&acc1_free, 4 * FM_NPART);
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -339,57 +414,76 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------- compute warps
+        // thread = (tile row r = TMEM lane, column part): CW = D / FM_NPART consecutive columns of the row, always
+        // handled in PIECES of 16 columns so that the register footprint stays ~3 x 16 values whatever D is.  A row of
+        // values that becomes the next MMA operand (x, S, H, x') is first stashed, fp32, in the already consumed
+        // columns of accumulator 0 (tensor memory is the only free storage of that size), because the operand's
+        // power-of-two scale needs the row maximum before the first element can be converted.
+        constexpr int CW = C::CW;
+        constexpr int NP = CW / 16;              // pieces per thread
         const int cw = warp - 4;
         const int q = cw & 3;                    // TMEM lane quarter this warp may touch (= warp % 4)
-        const int half = cw >> 2;                // which half of the columns
-        const int r = q * 32 + lane;             // tile row = TMEM lane
-        const int ct = threadIdx.x - 128;        // 0..255
+        const int part = cw >> 2;                // which part of the columns
+        const int col0 = part * CW;
+        // slot r = TMEM lane = operand row = row of the P_j buffer.  Tile-local graph rows are INTERLEAVED over the four
+        // lane quarters (row = lane * 4 + q): the warps of a quarter share one SM sub-partition (warp % 4), so a tile
+        // with few rows (one molecule per tile at B = 128) still spreads its work over all four schedulers
+        const int r = q * 32 + lane;
+        const int row_l = lane * 4 + q;
+        const int ct = threadIdx.x - 128;        // 0..FM_COMPUTE_THREADS-1
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const uint32_t STASH = ACC0 + lane_off;
         uint32_t n_full[2] = {0, 0};
         auto wait_acc = [&](int b) {
             fm_wait(&acc_full[b], n_full[b] & 1, 6 + b);
             ++n_full[b];
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         };
-        // values of this thread's CPT chunks -> fp16 (hi, lo) operand rows, scaled by the row's power of two; returns
-        // the inverse scale.  Leaves the operand visible to the tensor core and signals the MMA warp.
-        auto write_operand = [&](float (&val)[C::CPT][32]) -> float {
-            float m = 0.f;
-#pragma unroll
-            for (int ci = 0; ci < C::CPT; ++ci)
-#pragma unroll
-                for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(val[ci][j]));
-            rmax[half * FM_ROWS + r] = m;
+        // stashed row (columns [col0, col0 + CW) of accumulator 0, this thread's lane) -> fp16 (hi, lo) operand row scaled
+        // by the row's power of two; m = this thread's partial row maximum.  Returns the inverse scale, leaves the operand
+        // visible to the tensor core and signals the MMA warp.  `live` = the warp holds at least one valid row (other
+        // warps only take part in the barriers: their operand rows are never read back -- row i of a product depends on
+        // row i of the operand alone).
+        auto finish_operand = [&](float m, bool live) -> float {
+            if (live) rmax[part * FM_ROWS + r] = m;
             fm_bar_compute();
-            m = fmaxf(rmax[r], rmax[FM_ROWS + r]);
-            int e = (int)((__float_as_uint(m) >> 23) & 0xFF);                 // biased exponent of the row maximum
-            if (e == 0) e = 127 + 14;                                          // zero / denormal row: scale 1
-            int se = 127 + 14 - (e - 127);                                     // scale = 2^(14 - (e - 127))
-            se = max(1, min(254, se));
-            const float scale = __uint_as_float((uint32_t)se << 23);
-            const float inv = __uint_as_float((uint32_t)(254 - se) << 23);    // 2^-(se-127)
+            float inv = 1.f;
+            if (live) {
+                m = rmax[r];
 #pragma unroll
-            for (int ci = 0; ci < C::CPT; ++ci) {
-                const int col0 = (half * C::CPT + ci) * 32;
-                const int slab = col0 >> 6;
-                const int j0 = (col0 & 63) >> 3;
+                for (int pp = 1; pp < FM_NPART; ++pp) m = fmaxf(m, rmax[pp * FM_ROWS + r]);
+                int e = (int)((__float_as_uint(m) >> 23) & 0xFF);                 // biased exponent of the row maximum
+                if (e == 0) e = 127 + 14;                                          // zero / denormal row: scale 1
+                int se = 127 + 14 - (e - 127);                                     // scale = 2^(14 - (e - 127))
+                se = max(1, min(254, se));
+                const float scale = __uint_as_float((uint32_t)se << 23);
+                inv = __uint_as_float((uint32_t)(254 - se) << 23);                // 2^-(se-127)
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll 1
+                for (int pc = 0; pc < NP; ++pc) {
+                    const int c0 = col0 + 16 * pc;
+                    float v[16];
+                    fm_tmem_ld<16>(STASH + (uint32_t)c0, v);
+                    const int slab = c0 >> 6;
+                    const int j0 = (c0 & 63) >> 3;
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    uint32_t hi[4], lo[4];
+                    for (int jj = 0; jj < 2; ++jj) {
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float a = val[ci][jj * 8 + 2 * t] * scale, b = val[ci][jj * 8 + 2 * t + 1] * scale;
-                        const __half2 h2 = __floats2half2_rn(a, b);
-                        const float2 hf = __half22float2(h2);
-                        const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
-                        hi[t] = *reinterpret_cast<const uint32_t *>(&h2);
-                        lo[t] = *reinterpret_cast<const uint32_t *>(&l2);
+                        for (int t = 0; t < 4; ++t) {
+                            const float a = v[jj * 8 + 2 * t] * scale, b = v[jj * 8 + 2 * t + 1] * scale;
+                            const __half2 h2 = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(h2);
+                            const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+                            hi[t] = *reinterpret_cast<const uint32_t *>(&h2);
+                            lo[t] = *reinterpret_cast<const uint32_t *>(&l2);
+                        }
+                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)(((j0 + jj) ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + slab * C::SLAB + off), "r"(hi[0]),
+                                     "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + (C::KS + slab) * C::SLAB + off),
+                                     "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
                     }
-                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)(((j0 + jj) ^ (r & 7)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + slab * C::SLAB + off), "r"(hi[0]),
-                                 "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + (C::KS + slab) * C::SLAB + off),
-                                 "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -398,7 +492,51 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
             if (lane == 0) fm_arrive(&a_ready);
             return inv;
         };
+        auto absmax16 = [](float m, const float (&v)[16]) -> float {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, fabsf(v[j]));
+            return m;
+        };
+        // v (+)= 16 columns of a row of a swizzled shared-memory matrix / of a global-memory matrix
+        auto add_lds = [&](uint32_t base, int row, int c0, float (&v)[16]) {
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                float4 t;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                             : "r"(base + fm_swz<D>(row, c0 / 4 + i4)));
+                v[4 * i4] += t.x; v[4 * i4 + 1] += t.y; v[4 * i4 + 2] += t.z; v[4 * i4 + 3] += t.w;
+            }
+        };
+        auto add_ldg = [&](const float *rowp, int c0, float (&v)[16]) {
+            const float4 *t4 = reinterpret_cast<const float4 *>(rowp + c0);
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 t = __ldg(t4 + i4);
+                v[4 * i4] += t.x; v[4 * i4 + 1] += t.y; v[4 * i4 + 2] += t.z; v[4 * i4 + 3] += t.w;
+            }
+        };
+        auto sts16 = [&](uint32_t base, int row, int c0, const float (&v)[16]) {
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + fm_swz<D>(row, c0 / 4 + i4)), "f"(v[4 * i4]),
+                             "f"(v[4 * i4 + 1]), "f"(v[4 * i4 + 2]), "f"(v[4 * i4 + 3]) : "memory");
+        };
+        auto set16 = [&](const float *cvec, int c0, float (&v)[16]) {       // per-column constants (shared memory)
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 t = *reinterpret_cast<const float4 *>(cvec + c0 + 4 * i4);
+                v[4 * i4] = t.x; v[4 * i4 + 1] = t.y; v[4 * i4 + 2] = t.z; v[4 * i4 + 3] = t.w;
+            }
+        };
 
+        // constants of the first layer of the first tile; afterwards they are prefetched one layer ahead
+        constexpr int NVQ = FM_NV * D / 4;          // float4 of constants per layer
+        constexpr int NVT = (NVQ + FM_COMPUTE_THREADS - 1) / FM_COMPUTE_THREADS;
+        for (int i = ct; i < NVQ; i += FM_COMPUTE_THREADS)
+            reinterpret_cast<float4 *>(vecs)[i] = __ldg(reinterpret_cast<const float4 *>(P.layer[0].vec) + i);
+
+        bool first_tile = true;
+        (void)first_tile;
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
             const int gend = min(P.G, (u + 1) * P.unit);
             int g0 = u * P.unit;
@@ -411,27 +549,49 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
                 }
                 const int64_t row0 = __ldg(P.node_ptr + g0);
                 const int n_rows = (int)(__ldg(P.node_ptr + g1) - row0);
-                const bool valid = r < n_rows;
-                const int64_t grow = row0 + (valid ? r : 0);
+                const bool valid = row_l < n_rows;
+                const bool live = q < n_rows;               // warp-uniform: lane 0 holds the warp's smallest row
+                const int64_t grow = row0 + (valid ? row_l : 0);
                 const int e_begin = valid ? __ldg(P.rowptr + grow) : 0;
                 const int e_end = valid ? __ldg(P.rowptr + grow + 1) : 0;
                 const float deg = (float)(e_end - e_begin);
+                // neighbours of the first four in-edges, tile-local, 8 bits each (0xFF = outside the tile): fetched once
+                // per tile -- with ~227 KB of shared memory the SM has no L1 left, every global load is an L2 round trip
+                uint32_t nbr_pk = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (e_begin + i < e_end) {
+                        const int64_t jl = (int64_t)__ldg(P.nbr + e_begin + i) - row0;
+                        nbr_pk |= (uint32_t)((jl >= 0 && jl < n_rows) ? (((int)jl & 3) * 32 + ((int)jl >> 2)) : 0xFF) << (8 * i);
+                    }
+                }
                 float rx_inv = 1.f;       // inverse row scale of the operand currently in the A buffer
 
                 for (int l = 0; l < nL; ++l) {
                     const FmLayer &L = P.layer[l];
-                    // ---- per-layer constants into shared memory (previous layer's readers are past their last use:
-                    //      they arrived on a_ready after the x' epilogue; the barrier orders the overwrite)
-                    fm_bar_compute();
-                    for (int i = ct; i < FM_NV * D; i += FM_COMPUTE_THREADS) vecs[i] = __ldg(L.vec + i);
-                    // edge tables: 0 none / global, 1 small area, 2 the (still unused) operand buffer of a table-only layer
+                    FM_STAMP(l, 0);
+                    const int ng = L.n_edge_cols;
+                    // table rows of the first four in-edges, 16 bits each (up to 3 column groups)
+                    const bool rows_pk_ok = ng <= 3 && L.te_rows <= 65536;
+                    uint64_t rows_pk[3] = {0ull, 0ull, 0ull};       // [group]: 4 x 16 bits
+                    if (rows_pk_ok) {
+#pragma unroll
+                        for (int g = 0; g < 3; ++g)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (g < ng && e_begin + i < e_end)
+                                    rows_pk[g] |= (uint64_t)(uint32_t)__ldg(L.edge_rows + (int64_t)(e_begin + i) * ng + g) << (16 * i);
+                    }
+                    // edge tables: 0 global, 1 small area, 2 the (still unused) operand buffer of a table-only layer
                     int te_loc = 0;
                     const int te_bytes = L.te_rows * D * 4;
-                    if (L.n_edge_cols > 0) {
+                    if (ng > 0) {
                         if (te_bytes <= FM_TE_SMALL) te_loc = 1;
                         else if (!L.has_dense && te_bytes <= C::A_BYTES) te_loc = 2;
                     }
                     const uint32_t sTab = te_loc == 2 ? sA : sTE;
+                    // the previous layer's readers of the small table area / the constants are past their last use
+                    fm_bar_compute();
                     if (te_loc) {
                         const int nq = L.te_rows * (D / 4);
                         for (int i = ct; i < nq; i += FM_COMPUTE_THREADS) {
@@ -442,204 +602,192 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
                         }
                     }
                     if (l == 0 && L.has_dense) {
-                        // ---- dense input features: fp32 rows -> operand buffer
-                        float val[C::CPT][32];
+                        // ---- dense input features: fp32 rows -> operand buffer (accumulator 0 is free: stash, then convert)
+                        float m = 0.f;
+                        if (live) {
+#pragma unroll 1
+                            for (int pc = 0; pc < NP; ++pc) {
+                                const int c0 = col0 + 16 * pc;
+                                float v[16];
 #pragma unroll
-                        for (int ci = 0; ci < C::CPT; ++ci) {
-                            const int col0 = (half * C::CPT + ci) * 32;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                val[ci][j] = (valid && col0 + j < P.x0_d) ? __ldg(P.x0 + grow * P.x0_ld + col0 + j) : 0.f;
+                                for (int j = 0; j < 16; ++j)
+                                    v[j] = (valid && c0 + j < P.x0_d) ? __ldg(P.x0 + grow * P.x0_ld + c0 + j) : 0.f;
+                                m = absmax16(m, v);
+                                fm_tmem_st16(STASH + (uint32_t)c0, v);
+                            }
                         }
-                        rx_inv = write_operand(val);
+                        rx_inv = finish_operand(m, live);
                     }
-                    fm_bar_compute();          // vectors / tables staged
+                    fm_bar_compute();          // constants / tables staged
+                    FM_STAMP(l, 1);
 
                     // ---- P_j rows into shared memory
-                    {
-                        if (L.has_dense) wait_acc(1);
+                    if (L.has_dense) wait_acc(1);
+                    if (live) {
+#pragma unroll 1
+                        for (int pc = 0; pc < NP; ++pc) {
+                            const int c0 = col0 + 16 * pc;
+                            float v[16];
 #pragma unroll
-                        for (int ci = 0; ci < C::CPT; ++ci) {
-                            const int col0 = (half * C::CPT + ci) * 32;
-                            float v[32];
-                            if (L.has_dense) {
-                                fm_acc_ld<D>(ACC1 + lane_off, col0, v);
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] *= rx_inv * vecs[V_CJ * D + col0 + j];
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                            }
-                            if (valid) {
-                                for (int c = 0; c < L.n_node_cols; ++c) {
-                                    const int trow = __ldg(L.node_rows + grow * L.n_node_cols + c);
-                                    const float4 *t4 = reinterpret_cast<const float4 *>(L.Tn + (int64_t)trow * (2 * D) + D + col0);
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const float4 t = __ldg(t4 + i);
-                                        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sPJ + fm_swz<D>(r, col0 / 4 + i)),
-                                             "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
-                        }
-                        if (L.has_dense) {
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0) fm_arrive(&acc1_free);
+                            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                            if (L.has_dense) fm_acc_fma<D, 16>(ACC1 + lane_off, c0, rx_inv, vecs + V_CJ * D, v);
+                            if (valid)
+                                for (int c = 0; c < L.n_node_cols; ++c)
+                                    add_ldg(L.Tn + (int64_t)__ldg(L.node_rows + grow * L.n_node_cols + c) * (2 * D) + D, c0, v);
+                            sts16(sPJ, r, c0, v);
                         }
                     }
+                    if (L.has_dense) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) fm_arrive(&acc1_free);
+                    }
                     fm_bar_compute();          // every row of P_j visible
+                    FM_STAMP(l, 2);
 
-                    // ---- message phase: S_i = sum_e act(P_i + P_j[nbr] + sum_g Te[rows])
-                    float S[C::CPT][32];
-                    {
-                        if (L.has_dense) wait_acc(0);
-                        const int ng = L.n_edge_cols;
+                    // ---- message phase: S_i = sum_e act(P_i + P_j[nbr] + sum_g Te[rows]), 16 columns per pass over the
+                    //      row's in-edges; each finished piece replaces the consumed P_i piece in accumulator 0
+                    float m_s = 0.f;
+                    if (L.has_dense) wait_acc(0);
+                    FM_STAMP(l, 10);
+                    if (live) {
                         const int act = L.act_msg;
+#pragma unroll 1
+                        for (int pc = 0; pc < NP; ++pc) {
+                            const int c0 = col0 + 16 * pc;
+                            float p[16], S[16];
+                            set16(vecs + V_SHIFT * D, c0, p);
+                            if (L.has_dense) fm_acc_fma<D, 16>(ACC0 + lane_off, c0, rx_inv, vecs + V_CI * D, p);
+                            if (valid)
+                                for (int c = 0; c < L.n_node_cols; ++c)
+                                    add_ldg(L.Tn + (int64_t)__ldg(L.node_rows + grow * L.n_node_cols + c) * (2 * D), c0, p);
 #pragma unroll
-                        for (int ci = 0; ci < C::CPT; ++ci) {
-                            const int col0 = (half * C::CPT + ci) * 32;
-                            float p[32];
-                            if (L.has_dense) {
-                                fm_acc_ld<D>(ACC0 + lane_off, col0, p);
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    p[j] = fmaf(p[j], rx_inv * vecs[V_CI * D + col0 + j], vecs[V_SHIFT * D + col0 + j]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) p[j] = vecs[V_SHIFT * D + col0 + j];
-                            }
-                            if (valid) {
-                                for (int c = 0; c < L.n_node_cols; ++c) {
-                                    const int trow = __ldg(L.node_rows + grow * L.n_node_cols + c);
-                                    const float4 *t4 = reinterpret_cast<const float4 *>(L.Tn + (int64_t)trow * (2 * D) + col0);
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const float4 t = __ldg(t4 + i);
-                                        p[4 * i] += t.x; p[4 * i + 1] += t.y; p[4 * i + 2] += t.z; p[4 * i + 3] += t.w;
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) S[ci][j] = 0.f;
+                            for (int j = 0; j < 16; ++j) S[j] = 0.f;
                             for (int k = e_begin; k < e_end; ++k) {
-                                const int jl = (int)((int64_t)__ldg(P.nbr + k) - row0);
-                                if ((unsigned)jl >= (unsigned)n_rows) {
+                                const int i = k - e_begin;
+                                int jl;
+                                if (i < 4) jl = (int)((nbr_pk >> (8 * i)) & 0xFF);
+                                else {
+                                    const int64_t t = (int64_t)__ldg(P.nbr + k) - row0;
+                                    jl = (t >= 0 && t < n_rows) ? (((int)t & 3) * 32 + ((int)t >> 2)) : 0xFF;
+                                }
+                                if (jl == 0xFF) {
                                     atomicOr(P.status, GSN_S_CROSS_GRAPH_EDGE);
                                     continue;
                                 }
-                                float h[32];
+                                float h[16];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    float4 t;
-                                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                                                 : "r"(sPJ + fm_swz<D>(jl, col0 / 4 + i)));
-                                    h[4 * i] = p[4 * i] + t.x; h[4 * i + 1] = p[4 * i + 1] + t.y;
-                                    h[4 * i + 2] = p[4 * i + 2] + t.z; h[4 * i + 3] = p[4 * i + 3] + t.w;
-                                }
-                                for (int g = 0; g < ng; ++g) {
-                                    const int trow = __ldg(L.edge_rows + (int64_t)k * ng + g);
-                                    if (te_loc) {
+                                for (int j = 0; j < 16; ++j) h[j] = p[j];
+                                add_lds(sPJ, jl, c0, h);
+                                if (rows_pk_ok && i < 4) {
 #pragma unroll
-                                        for (int i = 0; i < 8; ++i) {
-                                            float4 t;
-                                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                                                         : "r"(sTab + fm_swz<D>(trow, col0 / 4 + i)));
-                                            h[4 * i] += t.x; h[4 * i + 1] += t.y; h[4 * i + 2] += t.z; h[4 * i + 3] += t.w;
+                                    for (int g = 0; g < 3; ++g) {
+                                        if (g < ng) {
+                                            const int tr = (int)((rows_pk[g] >> (16 * i)) & 0xFFFF);
+                                            if (te_loc) add_lds(sTab, tr, c0, h);
+                                            else add_ldg(L.Te + (int64_t)tr * D, c0, h);
                                         }
-                                    } else {
-                                        const float4 *t4 = reinterpret_cast<const float4 *>(L.Te + (int64_t)trow * D + col0);
-#pragma unroll
-                                        for (int i = 0; i < 8; ++i) {
-                                            const float4 t = __ldg(t4 + i);
-                                            h[4 * i] += t.x; h[4 * i + 1] += t.y; h[4 * i + 2] += t.z; h[4 * i + 3] += t.w;
-                                        }
+                                    }
+                                } else {
+                                    for (int g = 0; g < ng; ++g) {
+                                        const int tr = __ldg(L.edge_rows + (int64_t)k * ng + g);
+                                        if (te_loc) add_lds(sTab, tr, c0, h);
+                                        else add_ldg(L.Te + (int64_t)tr * D, c0, h);
                                     }
                                 }
                                 if (act == 0) {
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) S[ci][j] += fmaxf(h[j], 0.f);
+                                    for (int j = 0; j < 16; ++j) S[j] += fmaxf(h[j], 0.f);
                                 } else {
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) S[ci][j] += fm_act(h[j], act);
+                                    for (int j = 0; j < 16; ++j) S[j] += fm_act(h[j], act);
                                 }
                             }
+                            m_s = absmax16(m_s, S);
+                            __syncwarp();          // lanes leave the edge loop at different trip counts; the store is warp-wide
+                            fm_tmem_st16(STASH + (uint32_t)c0, S);
                         }
                     }
+                    FM_STAMP(l, 3);
                     // the operand buffer may be overwritten once Ux (the last GEMM reading x) has completed; a table-only
-                    // layer has no GEMM in flight, but its tables may sit in the operand buffer: write_operand's barrier
+                    // layer has no GEMM in flight, but its tables may sit in the operand buffer: finish_operand's barrier
                     // (every thread is past its message loop) orders that
                     if (L.has_dense) wait_acc(1);
-                    const float rs_inv = write_operand(S);
+                    FM_STAMP(l, 4);
+                    const float rs_inv = finish_operand(m_s, live);
+                    FM_STAMP(l, 5);
 
                     // ---- update epilogue: H = act((Ux + S Wf^T + deg vf + c1 [+ Tu]) su + tu)
                     float rh_inv;
                     {
+                        // row of the one-hot input's update table: requested before the GEMM wait
+                        const float *tu_row = (L.Tu && valid) ? L.Tu + (int64_t)__ldg(L.tu_rows + grow * L.tu_stride) * D : nullptr;
                         wait_acc(0);
-                        float H[C::CPT][32];
-                        const int act = L.act_upd;
+                        FM_STAMP(l, 6);
+                        float m = 0.f;
+                        if (live) {
+                            const int act = L.act_upd;
+#pragma unroll 1
+                            for (int pc = 0; pc < NP; ++pc) {
+                                const int c0 = col0 + 16 * pc;
+                                float H[16];
 #pragma unroll
-                        for (int ci = 0; ci < C::CPT; ++ci) {
-                            const int col0 = (half * C::CPT + ci) * 32;
-                            fm_acc_ld<D>(ACC0 + lane_off, col0, H[ci]);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                H[ci][j] = fmaf(H[ci][j], rs_inv * vecs[V_CF * D + col0 + j],
-                                                fmaf(deg, vecs[V_CV * D + col0 + j], vecs[V_CB * D + col0 + j]));
-                            if (L.has_dense) {
-                                float uacc[32];
-                                fm_acc_ld<D>(ACC1 + lane_off, col0, uacc);
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) H[ci][j] = fmaf(uacc[j], rx_inv * vecs[V_CU * D + col0 + j], H[ci][j]);
-                            }
-                            if (L.Tu && valid) {
-                                const int trow = __ldg(L.tu_rows + grow * L.tu_stride);
-                                const float4 *t4 = reinterpret_cast<const float4 *>(L.Tu + (int64_t)trow * D + col0);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 t = __ldg(t4 + i);
-                                    H[ci][4 * i] += t.x; H[ci][4 * i + 1] += t.y; H[ci][4 * i + 2] += t.z; H[ci][4 * i + 3] += t.w;
+                                for (int i4 = 0; i4 < 4; ++i4) {
+                                    const float4 cv = *reinterpret_cast<const float4 *>(vecs + V_CV * D + c0 + 4 * i4);
+                                    const float4 cb = *reinterpret_cast<const float4 *>(vecs + V_CB * D + c0 + 4 * i4);
+                                    H[4 * i4] = fmaf(deg, cv.x, cb.x); H[4 * i4 + 1] = fmaf(deg, cv.y, cb.y);
+                                    H[4 * i4 + 2] = fmaf(deg, cv.z, cb.z); H[4 * i4 + 3] = fmaf(deg, cv.w, cb.w);
                                 }
-                            }
-                            if (act == 0) {
+                                fm_acc_fma<D, 16>(ACC0 + lane_off, c0, rs_inv, vecs + V_CF * D, H);
+                                if (L.has_dense) fm_acc_fma<D, 16>(ACC1 + lane_off, c0, rx_inv, vecs + V_CU * D, H);
+                                if (tu_row) add_ldg(tu_row, c0, H);
+                                if (act == 0) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) H[ci][j] = valid ? fmaxf(H[ci][j], 0.f) : 0.f;
-                            } else {
+                                    for (int j = 0; j < 16; ++j) H[j] = valid ? fmaxf(H[j], 0.f) : 0.f;
+                                } else {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) H[ci][j] = valid ? fm_act(H[ci][j], act) : 0.f;
+                                    for (int j = 0; j < 16; ++j) H[j] = valid ? fm_act(H[j], act) : 0.f;
+                                }
+                                m = absmax16(m, H);
+                                fm_tmem_st16(STASH + (uint32_t)c0, H);
                             }
                         }
-                        rh_inv = write_operand(H);
+                        rh_inv = finish_operand(m, live);
+                        FM_STAMP(l, 7);
                     }
 
                     // ---- output epilogue: x' = act((H U2^T + c2) sm + tm), readout, next layer's operand
                     {
+                        // constants of the next layer in sequence (the first layer of the next tile after the last one)
+                        const FmLayer &Ln = P.layer[l + 1 < nL ? l + 1 : 0];
+                        float4 vnext[NVT];
+#pragma unroll
+                        for (int i = 0; i < NVT; ++i)
+                            if (ct + i * FM_COMPUTE_THREADS < NVQ)
+                                vnext[i] = __ldg(reinterpret_cast<const float4 *>(Ln.vec) + ct + i * FM_COMPUTE_THREADS);
                         wait_acc(0);
-                        float X[C::CPT][32];
-                        const int act = L.act_out;
+                        FM_STAMP(l, 8);
+                        float m = 0.f;
+                        if (live) {
+                            const int act = L.act_out;
+#pragma unroll 1
+                            for (int pc = 0; pc < NP; ++pc) {
+                                const int c0 = col0 + 16 * pc;
+                                float X[16];
+                                set16(vecs + V_C2B * D, c0, X);
+                                fm_acc_fma<D, 16>(ACC0 + lane_off, c0, rh_inv, vecs + V_C2S * D, X);
 #pragma unroll
-                        for (int ci = 0; ci < C::CPT; ++ci) {
-                            const int col0 = (half * C::CPT + ci) * 32;
-                            fm_acc_ld<D>(ACC0 + lane_off, col0, X[ci]);
+                                for (int j = 0; j < 16; ++j) X[j] = valid ? fm_act(X[j], act) : 0.f;
+                                if (L.x_out && valid) {
+                                    float4 *o4 = reinterpret_cast<float4 *>(L.x_out + grow * D + c0);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float v = fmaf(X[ci][j], rh_inv * vecs[V_C2S * D + col0 + j], vecs[V_C2B * D + col0 + j]);
-                                X[ci][j] = valid ? fm_act(v, act) : 0.f;
-                            }
-                            if (L.x_out && valid) {
-                                float4 *o4 = reinterpret_cast<float4 *>(L.x_out + grow * D + col0);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) o4[i] = make_float4(X[ci][4 * i], X[ci][4 * i + 1], X[ci][4 * i + 2], X[ci][4 * i + 3]);
-                            }
-                            if (L.pool) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sPJ + fm_swz<D>(r, col0 / 4 + i)),
-                                                 "f"(X[ci][4 * i]), "f"(X[ci][4 * i + 1]), "f"(X[ci][4 * i + 2]), "f"(X[ci][4 * i + 3]) : "memory");
+                                    for (int i4 = 0; i4 < 4; ++i4) o4[i4] = make_float4(X[4 * i4], X[4 * i4 + 1], X[4 * i4 + 2], X[4 * i4 + 3]);
+                                }
+                                if (L.pool) sts16(sPJ, r, c0, X);
+                                if (l + 1 < nL) {
+                                    m = absmax16(m, X);
+                                    fm_tmem_st16(STASH + (uint32_t)c0, X);
+                                }
                             }
                         }
                         if (L.pool) {
@@ -652,16 +800,22 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
                                 float acc = 0.f;
                                 for (int rr = ra; rr < rb; ++rr) {
                                     float t;
-                                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sPJ + fm_swz<D>(rr, col >> 2) + (uint32_t)((col & 3) << 2)));
+                                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sPJ + fm_swz<D>((rr & 3) * 32 + (rr >> 2), col >> 2) + (uint32_t)((col & 3) << 2)));
                                     acc += t;
                                 }
                                 if (L.pool == 2 && rb > ra) acc /= (float)(rb - ra);
                                 L.pooled[(int64_t)g * D + col] = acc;
                             }
                         }
-                        if (l + 1 < nL) rx_inv = write_operand(X);
+                        if (l + 1 < nL) rx_inv = finish_operand(m, live);
+                        else fm_bar_compute();          // every reader of this layer's constants is done
+#pragma unroll
+                        for (int i = 0; i < NVT; ++i)
+                            if (ct + i * FM_COMPUTE_THREADS < NVQ) reinterpret_cast<float4 *>(vecs)[ct + i * FM_COMPUTE_THREADS] = vnext[i];
+                        FM_STAMP(l, 9);
                     }
                 }
+                first_tile = false;
                 g0 = g1;
             }
         }
@@ -708,7 +862,7 @@ static int fm_launch(const CUtensorMap &hi, const CUtensorMap &lo, const FmParam
     constexpr int smem = FmCfg<D>::SMEM;
     GSN_CUDA_OK(cudaFuncSetAttribute(fused_model_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned grid = (unsigned)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
-    fused_model_kernel<D><<<grid, 384, smem, stream>>>(hi, lo, p);
+    fused_model_kernel<D><<<grid, FM_THREADS, smem, stream>>>(hi, lo, p);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("fused_model_kernel");
     return GSN_OK;
@@ -717,6 +871,13 @@ static int fm_launch(const CUtensorMap &hi, const CUtensorMap &lo, const FmParam
 }  // namespace gsn
 
 using namespace gsn;
+
+#ifdef GSN_PROFILE_STAMPS
+extern "C" int gsn_fm_profile_read(long long *h_out) {
+    GSN_CUDA_OK(cudaMemcpyFromSymbol(h_out, g_fm_stamps, sizeof(long long) * FM_MAX_LAYERS * 16));
+    return GSN_OK;
+}
+#endif
 
 extern "C" int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream_) {
     if (!h_m) return GSN_E_INVALID;

@@ -2,9 +2,12 @@
 
 Same constructor and the same parameter names (fc.{i}.*, bn.{i}.*) as
 /root/reference/models_misc.py:18-59, so reference checkpoints load unchanged.
-The GEMMs themselves are plain library GEMMs (cuBLAS through torch, TF32 off);
-what this class adds over the reference are the accessors the fused message
-kernels use (first-layer split, BatchNorm as scale/shift).
+Inference on CUDA tensors runs on the library's own dense-tail kernel
+(gsn_tc_linear_fwd: tcgen05 3xTF32 with bias, eval-mode BatchNorm as scale/shift
+and the activation in the epilogue; `forward(x, x2)` multiplies cat(x, x2)
+without materialising the cat).  Training (autograd) and CPU tensors use the
+torch modules (cuBLAS SGEMM, TF32 off).  The class also exposes the accessors
+the fused message kernels use (first-layer split, BatchNorm as scale/shift).
 """
 from __future__ import annotations
 
@@ -48,7 +51,29 @@ class mlp(nn.Module):
             x = self.bn[i](x)
         return self.activation(x)
 
-    def forward(self, x):
+    def _own_kernels(self, x) -> bool:
+        """eval / no-grad forward on a CUDA tensor: nothing to differentiate, BatchNorm is a fixed affine"""
+        if not x.is_cuda or x.dim() != 2 or x.shape[0] == 0:
+            return False
+        if self.batch_norm and self.training:
+            return False
+        return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
+
+    def forward(self, x, x2=None):
+        """x2: optional second input block; the result equals forward(cat(x, x2, -1)) (models_misc.py:52-59)"""
+        if self._own_kernels(x):
+            from . import ops
+            x = x.float().contiguous()
+            x2 = None if x2 is None else x2.float().contiguous()
+            with torch.no_grad():
+                for i in range(len(self.fc) - 1):
+                    s, t = self.bn_affine(i)
+                    x = ops.linear(x, self.fc[i].weight, bias=self.fc[i].bias, A2=x2, scale=s, shift=t,
+                                   activation=self.activation_name)
+                    x2 = None
+                return ops.linear(x, self.fc[-1].weight, bias=self.fc[-1].bias, A2=x2)
+        if x2 is not None:
+            x = torch.cat((x, x2), -1)
         for i in range(len(self.fc) - 1):
             x = self.hidden(x, i)
         return self.fc[-1](x)
@@ -61,6 +86,20 @@ class mlp(nn.Module):
             return None, None
         bn = self.bn[i]
         if batch_stats is None:
+            # eval: a fixed affine, cached until the module's tensors change (no elementwise launches per forward)
+            stamp = (bn.running_mean.data_ptr(), bn.running_mean._version, bn.running_var._version,
+                     bn.weight._version if bn.affine else 0, bn.bias._version if bn.affine else 0)
+            cache = self.__dict__.setdefault('_affine_cache', {})
+            hit = cache.get(i)
+            if hit is not None and hit[0] == stamp:
+                return hit[1], hit[2]
+            with torch.no_grad():
+                inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+                scale = (bn.weight * inv if bn.affine else inv).contiguous()
+                shift = ((bn.bias if bn.affine else 0) - bn.running_mean.float() * scale).contiguous()
+            if not (torch.is_grad_enabled() and bn.affine and bn.weight.requires_grad):
+                cache[i] = (stamp, scale, shift)
+                return scale, shift
             mean, var = bn.running_mean, bn.running_var
         else:
             mean, var, count = batch_stats

@@ -90,10 +90,10 @@ class GSNPipeline:
         with torch.cuda.stream(self._side):
             flow = self.model.conv[0].flow
             ops.edge_plan(t['edge_index'], N, flow).degree()
-        graph = counting.BatchedGraph(t['edge_index'], t['node_ptr'], num_nodes=N, max_nodes_per_graph=self.max_nodes)
+        status = torch.zeros(1, dtype=torch.int32, device=t['edge_index'].device)
         ids = counting.count_batch(t['edge_index'], t['node_ptr'], self.subgraph_dicts, self.induced, self.id_scope,
-                                   num_nodes=N, max_nodes_per_graph=self.max_nodes, check=False, graph=graph)
-        self.last_status = graph.status
+                                   num_nodes=N, max_nodes_per_graph=self.max_nodes, check=False, status=status)
+        self.last_status = status
         cur.wait_stream(self._side)
         if self.fused is not None:
             data = Batch(x=t['x'], edge_index=t['edge_index'], edge_features=t['edge_features'], batch=t['batch'],
@@ -133,3 +133,138 @@ class GSNPipeline:
     def replay(self) -> torch.Tensor:
         self._graph.replay()
         return self._out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# variable-shape batches through captured CUDA graphs
+# ---------------------------------------------------------------------------------------------------------------------
+FIELDS = ('edge_index', 'node_ptr', 'x', 'edge_features', 'batch', 'degrees')
+
+
+class Packing:
+    """byte layout of one (padded) batch inside a single buffer, 16-byte aligned fields: a step's inputs move with ONE
+    copy (device to device, or pinned host to device)"""
+
+    def __init__(self, shapes: Dict[str, tuple], dtypes: Dict[str, torch.dtype]):
+        self.fields, off = [], 0
+        for k in FIELDS:
+            n = 1
+            for d in shapes[k]:
+                n *= int(d)
+            nbytes = n * torch.empty((), dtype=dtypes[k]).element_size()
+            self.fields.append((k, off, nbytes, dtypes[k], tuple(int(d) for d in shapes[k])))
+            off += (nbytes + 15) // 16 * 16
+        self.nbytes = off
+
+    def views(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {k: buf[off:off + n].view(dt).view(shape) for k, off, n, dt, shape in self.fields}
+
+    def pack(self, t: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tensors (CPU) -> one uint8 buffer"""
+        if out is None:
+            out = torch.zeros(self.nbytes, dtype=torch.uint8)
+        for k, off, n, dt, shape in self.fields:
+            out[off:off + n] = t[k].contiguous().view(-1).view(torch.uint8)
+        return out
+
+
+class BucketedPipeline:
+    """The reference's DataLoader (main.py:243-258) yields a different (N, E) every step, a captured CUDA graph needs
+    static shapes.  Batches are therefore padded to BUCKET shapes and every bucket owns one captured GSNPipeline step
+    (an LRU of `max_buckets` of them):
+
+      * nodes  N -> N_cap: the padding rows form extra `sentinel` graphs (<= pad_graph_nodes nodes each, G_cap - G of
+        them, possibly empty) after the real ones -- graphs are independent in COUNT, in message passing and in the
+        readout, so the real graphs' predictions are unchanged and the sentinels' rows are dropped;
+      * edges  E -> E_cap: the padding columns are self loops on sentinel nodes (at most 4 per node).  COUNT drops self
+        loops like remove_self_loops (utils_ids.py:11-15), message passing only sends them to sentinel rows;
+      * graphs G -> G_cap = G + a fixed number of sentinel graphs (so that the shape depends on the bucket only).
+
+    pad() works on host arrays (it is part of collating a batch); run() copies one packed buffer into the bucket's
+    static inputs and replays its graph."""
+
+    def __init__(self, model, subgraph_dicts, induced: bool, id_scope: str, encoder: UniqueEncoder, max_nodes_per_graph: int,
+                 node_step: int = 128, edge_step: int = 256, max_buckets: int = 16, fused=True):
+        self.args = (model, subgraph_dicts, induced, id_scope, encoder, int(max_nodes_per_graph))
+        self.fused = fused
+        self.node_step, self.edge_step, self.max_buckets = int(node_step), int(edge_step), int(max_buckets)
+        self.pad_graph_nodes = min(64, int(max_nodes_per_graph))
+        self._lru: 'OrderedDict[tuple, tuple]' = __import__('collections').OrderedDict()
+        self.captures = 0
+
+    # ---- shapes
+    def bucket(self, N: int, E: int, G: int):
+        """(N_cap, E_cap, G_cap) of a batch with N nodes, E edge columns, G graphs"""
+        E_cap = -(-max(E, 1) // self.edge_step) * self.edge_step
+        need_nodes = max(1, -(-(E_cap - E) // 4))                       # <= 4 padding self loops per sentinel node
+        N_cap = -(-(N + need_nodes) // self.node_step) * self.node_step
+        # sentinel graphs: enough for the largest padding a bucket can see
+        max_pad_nodes = self.node_step + -(-self.edge_step // 4)
+        G_cap = G + -(-max_pad_nodes // self.pad_graph_nodes) + 1
+        return N_cap, E_cap, G_cap
+
+    def pad(self, b: Dict, bucket=None) -> Dict[str, torch.Tensor]:
+        """numpy / tensor batch (fields FIELDS) -> padded CPU tensors of the bucket's shapes"""
+        import numpy as np
+        t = {k: (torch.from_numpy(np.ascontiguousarray(b[k])) if not torch.is_tensor(b[k]) else b[k].cpu()) for k in FIELDS}
+        N, E, G = int(t['x'].shape[0]), int(t['edge_index'].shape[1]), int(t['node_ptr'].numel() - 1)
+        N_cap, E_cap, G_cap = bucket or self.bucket(N, E, G)
+        pn, pe = N_cap - N, E_cap - E
+        if pn < max(1, -(-pe // 4)) or pe < 0 or G_cap <= G:
+            raise ValueError('batch does not fit the bucket')
+        out = {}
+        loops = N + (torch.arange(pe, dtype=torch.int64) // 4)
+        out['edge_index'] = torch.cat((t['edge_index'], torch.stack((loops, loops))), 1)
+        ptr = torch.full((G_cap + 1,), N_cap, dtype=torch.int64)
+        ptr[:G + 1] = t['node_ptr']
+        k = torch.arange(1, G_cap - G + 1, dtype=torch.int64)
+        ptr[G + 1:] = torch.clamp(N + k * self.pad_graph_nodes, max=N_cap)
+        if int(ptr[-1]) != N_cap:
+            raise ValueError('not enough sentinel graphs for this padding')
+        out['node_ptr'] = ptr
+        xs = t['x']
+        out['x'] = torch.cat((xs, torch.zeros((pn,) + tuple(xs.shape[1:]), dtype=xs.dtype)), 0)
+        ef = t['edge_features']
+        out['edge_features'] = torch.cat((ef, torch.ones((pe,) + tuple(ef.shape[1:]), dtype=ef.dtype)), 0)
+        sizes = ptr[1:] - ptr[:-1]
+        out['batch'] = torch.repeat_interleave(torch.arange(G_cap, dtype=torch.int64), sizes)
+        dg = t['degrees']
+        out['degrees'] = torch.cat((dg, torch.zeros((pn,) + tuple(dg.shape[1:]), dtype=dg.dtype)), 0)
+        return out
+
+    def packing(self, padded: Dict[str, torch.Tensor]) -> Packing:
+        return Packing({k: tuple(v.shape) for k, v in padded.items()}, {k: v.dtype for k, v in padded.items()})
+
+    # ---- captured step per bucket
+    def _entry(self, key, padded_example: Dict[str, torch.Tensor], device):
+        ent = self._lru.get(key)
+        if ent is not None:
+            self._lru.move_to_end(key)
+            return ent
+        model, sds, induced, scope, enc, mx = self.args
+        pk = self.packing(padded_example)
+        buf = torch.zeros(pk.nbytes, dtype=torch.uint8, device=device)
+        pipe = GSNPipeline(model, sds, induced, scope, enc, mx, fused=self.fused)
+        pipe.capture({k: v.to(device) for k, v in padded_example.items()}, warmup=2, static=pk.views(buf))
+        ent = (pipe, pk, buf)
+        self._lru[key] = ent
+        self.captures += 1
+        while len(self._lru) > self.max_buckets:
+            self._lru.popitem(last=False)
+        return ent
+
+    def prepare(self, b: Dict, device, pin: bool = False):
+        """collate-time half of a step: pad + pack one batch.  Returns (bucket key, packed uint8 buffer on the CPU
+        [pinned], number of real graphs) and makes sure the bucket's graph is captured."""
+        padded = self.pad(b)
+        key = (padded['x'].shape[0], padded['edge_index'].shape[1], padded['node_ptr'].numel() - 1)
+        _, pk, _ = self._entry(key, padded, device)
+        packed = pk.pack(padded)
+        return key, (packed.pin_memory() if pin else packed), int(b['node_ptr'].shape[0] - 1)
+
+    def run(self, key, packed: torch.Tensor, n_graphs: int) -> torch.Tensor:
+        """one step: copy the packed inputs (host or device) into the bucket's static buffer, replay; the returned
+        tensor is a view of the bucket's static output (valid until the bucket runs again)"""
+        pipe, pk, buf = self._lru[key]
+        buf.copy_(packed, non_blocking=True)
+        return pipe.replay()[:n_graphs]

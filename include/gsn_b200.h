@@ -51,6 +51,8 @@ extern "C" {
 #define GSN_S_MISSING_EDGE 4    /* edge scope: a match used (a,b) but edge_index has no column (a,b)
                                    (utils_graph_processing.py:173 raises KeyError) */
 #define GSN_S_INDEX_RANGE 8     /* a node id outside [0,N) */
+#define GSN_S_COUNT_OVERFLOW 16 /* a per-vertex / per-edge count exceeded 2^32 - 1 inside a CTA-private accumulator */
+#define GSN_S_NOT_GROUPED 32    /* gsn_count_small: edge_index columns are not grouped by graph (PyG collate order) */
 
 #define GSN_MAXK 16             /* max pattern vertices */
 
@@ -123,6 +125,20 @@ int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t W, const i
                       const int64_t *d_node_ptr, int64_t G, const GsnPlan *h_plan, int64_t *d_out,
                       int64_t out_ld, void *d_scratch, size_t scratch_bytes, int32_t *d_status,
                       void *stream);
+
+/*
+ * COUNT for batches of SMALL graphs (every graph <= 64 nodes) in ONE launch and without a workspace: graph build
+ * (gsn_graph_build), enumeration (gsn_count_pattern) and the write-out in edge_index order happen inside one kernel,
+ * CTA-private in shared memory.  Same outputs as gsn_graph_build + gsn_count_pattern.  Cycle families run a
+ * warp-cooperative depth-first search (shared frame stack, ballot / popc compaction; kmax <= 12), cliques and
+ * generic patterns the per-thread bitmask search.
+ * Requires the columns of edge_index to be grouped by graph in batch order (what PyG's collate produces):
+ * the columns of a run of graphs are located by binary search on the source row; a batch that violates this sets
+ * GSN_S_NOT_GROUPED (the caller falls back to gsn_graph_build + gsn_count_pattern).  A graph with more than 64 nodes
+ * sets GSN_S_GRAPH_TOO_LARGE.  Returns GSN_E_UNSUPPORTED for plans outside the kernel (cycles with kmax > 12).
+ */
+int gsn_count_small(const int64_t *d_edge_index, int64_t E, const int64_t *d_node_ptr, int64_t G, int64_t N,
+                    const GsnPlan *h_plan, int64_t *d_out, int64_t out_ld, int32_t *d_status, void *stream);
 
 /* ------------------------------------------------------------------ */
 /* MP                                                                  */

@@ -17,6 +17,7 @@ struct HostAcc {
     int ld, col0;
     void vertex(int lv, int col, uint32_t c) { v[(size_t)lv * ld + col0 + col] += c; }
     void slot(int sl, int col, uint32_t c) { s[(size_t)sl * ld + col0 + col] += c; }
+    void overflow() {}
 };
 
 template <int W>
