@@ -119,31 +119,40 @@ def test_shards_partition_the_dataset():
                 assert torch.equal(getattr(a, k), getattr(b, k)), (world, k)
 
 
-def test_bench_batch_variants_and_packing():
-    """bench.py helpers: the pooled batches keep the shapes of the base batch (CUDA graphs need static shapes),
-    hold the same graphs in another order, and survive the single-buffer packing bit for bit"""
+def test_bucket_padding_and_packing():
+    """BucketedPipeline.pad (host side of the shape-bucketed capture): sentinel graphs hold the padding nodes, padding
+    edge columns are self loops on sentinel nodes (<= 4 per node), the real batch is untouched, shapes depend on the
+    bucket only, and the single-buffer packing round-trips bit for bit"""
     import bench
-    b = bench.build_batches(16, 1, seed0=3)[0]
-    v = bench.batch_variants(b, 3, seed=1)
-    keys = ('edge_index', 'node_ptr', 'x', 'edge_features', 'batch', 'degrees')
-    for i in range(3):
-        ei, nptr, bt = v['edge_index'][i].numpy(), v['node_ptr'][i].numpy(), v['batch'][i].numpy()
-        assert ei.shape == b['edge_index'].shape and sorted(np.diff(nptr)) == sorted(np.diff(b['node_ptr']))
-        g0 = np.searchsorted(nptr, ei[0], side='right') - 1
-        g1 = np.searchsorted(nptr, ei[1], side='right') - 1
-        assert (g0 == g1).all() and (bt[ei[0]] == g0).all()
-        pairs = set(map(tuple, ei.T.tolist()))
-        assert all((q, p) in pairs for p, q in pairs)                      # still symmetric
-        assert (v['degrees'][i].numpy() == np.bincount(ei[0], minlength=int(nptr[-1]))).all()
-    assert not np.array_equal(v['edge_index'][0].numpy(), v['edge_index'][1].numpy())
-    pk = bench.Packing({k: v[k][0] for k in keys})
-    pool = pk.pack_pool(v)
-    buf = torch.zeros(pk.nbytes, dtype=torch.uint8)
-    views = pk.views(buf)
-    for i in range(3):
-        buf.copy_(pool[i])
-        for k in keys:
-            assert torch.equal(views[k], v[k][i]), k
+    from gsn_b200.pipeline import BucketedPipeline, FIELDS
+    bp = BucketedPipeline(None, None, False, 'local', None, 64, node_step=64, edge_step=128)
+    seen = {}
+    for seed in range(8):
+        b = bench.build_batches(16, 1, seed0=seed)[0]
+        N, E, G = int(b['node_ptr'][-1]), b['edge_index'].shape[1], 16
+        N_cap, E_cap, G_cap = bp.bucket(N, E, G)
+        assert N_cap % 64 == 0 and E_cap % 128 == 0 and N_cap > N and E_cap >= E and G_cap > G
+        p = bp.pad(b)
+        assert p['x'].shape[0] == N_cap and p['edge_index'].shape == (2, E_cap) and p['node_ptr'].numel() == G_cap + 1
+        assert p['batch'].shape[0] == N_cap and p['degrees'].shape[0] == N_cap and p['edge_features'].shape[0] == E_cap
+        for k in FIELDS:
+            n = {'edge_index': E, 'node_ptr': G + 1, 'edge_features': E}.get(k, N)
+            real = p[k][:, :n] if k == 'edge_index' else p[k][:n]
+            assert np.array_equal(real.numpy(), b[k]), k
+        ptr = p['node_ptr'].numpy()
+        assert ptr[-1] == N_cap and (np.diff(ptr) >= 0).all() and np.diff(ptr)[G:].max() <= 64
+        pad_e = p['edge_index'][:, E:].numpy()
+        assert (pad_e[0] == pad_e[1]).all() and (pad_e >= N).all() and (pad_e < N_cap).all()
+        if pad_e.shape[1]:
+            assert np.bincount(pad_e[0] - N).max() <= 4
+        assert np.array_equal(p['batch'].numpy(), np.repeat(np.arange(G_cap), np.diff(ptr)))
+        pk = bp.packing(p)
+        buf = pk.pack(p)
+        views = pk.views(buf)
+        for k in FIELDS:
+            assert torch.equal(views[k], p[k]), k
+        seen.setdefault((N_cap, E_cap, G_cap), pk.nbytes)
+        assert seen[(N_cap, E_cap, G_cap)] == pk.nbytes              # layout is a function of the bucket
 
 
 def test_flat_loader_batches_equal_collate_over_the_same_order():

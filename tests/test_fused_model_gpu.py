@@ -150,3 +150,38 @@ def test_one_kernel_rejects_oversized_graphs():
     model, b, _ = _golden_model('zinc_gsne_general')
     assert not fused_model.supported(model, max_nodes_per_graph=129)
     assert fused_model.supported(model, max_nodes_per_graph=128)
+
+
+def test_bucketed_pipeline_variable_shapes():
+    """the reference's DataLoader yields a different (N, E) every step (main.py:243-258): batches padded to shape
+    buckets (sentinel graphs, self loops) and replayed through captured CUDA graphs give the eager results on the
+    unpadded batch, and revisiting a bucket does not capture again"""
+    import bench
+    from gsn_b200.pipeline import BucketedPipeline, GSNPipeline
+    from gsn_b200.synthetic import zinc_like_batch
+    model, sds, enc, _, _, _ = _zinc_setup(64, 3)
+    dev = torch.device('cuda')
+    bp = BucketedPipeline(model, sds, False, 'local', enc, 64, node_step=64, edge_step=128)
+    eager = GSNPipeline(model, sds, False, 'local', enc, 64)
+    raws = [zinc_like_batch(48, seed=100 + i) for i in range(6)] + [zinc_like_batch(17, seed=7)]
+    shapes = {(int(b['node_ptr'][-1]), b['edge_index'].shape[1]) for b in raws}
+    assert len(shapes) == len(raws)                                  # genuinely different batches
+    outs = []
+    for rnd in range(2):
+        for i, b in enumerate(raws):
+            key, packed, G = bp.prepare(b, dev, pin=(i % 2 == 0))
+            out = bp.run(key, packed.to(dev) if i % 3 == 0 else packed, G).clone()
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                exp = eager.step(bench.to_tensors(b, device=dev))
+            assert out.shape == exp.shape
+            scale = max(float(exp.abs().max()), 1.0)
+            torch.testing.assert_close(out, exp, atol=TOL * scale, rtol=TOL)
+            assert int(bp._lru[key][0].last_status.item()) == 0
+            outs.append(out)
+        if rnd == 0:
+            first = bp.captures
+    assert bp.captures == first <= len(raws)
+    # padding never leaks: a batch alone and the same batch after another one of the bucket give identical bits
+    for a, b_ in zip(outs[:len(raws)], outs[len(raws):]):
+        assert torch.equal(a, b_)
