@@ -1,0 +1,237 @@
+// Training-step kernels of the ogbg-molhiv recipe (BASELINE config 3):
+//
+//   * embedding bag over categorical columns, forward and backward: the sum of per-column nn.Embedding lookups of
+//     multi_embedding (aggr 'sum', utils_graph_learning.py:134-167 -- 72 identifier columns in the molhiv recipe) and of
+//     ogb's AtomEncoder / BondEncoder (9 / 3 columns) in ONE launch each way instead of one lookup + one add (forward)
+//     and one scatter per column (backward);
+//   * backward of the 'ogb' message kind (GSN_edge_sparse_ogb.py:86-129 through autograd): one pass over the edges
+//     grouped by SOURCE node recomputes the relu mask from the layer inputs and produces the gradients w.r.t. x
+//     (identifiers) and the per-edge features -- no [E, d] tensor is saved by the forward.
+#include "common.cuh"
+
+namespace gsn {
+
+struct BagParams {
+    const float *tab[GSN_MAX_BAG_COLS];     // forward: tables; backward: gradient tables (zero-initialised by the caller)
+    int32_t rows_of[GSN_MAX_BAG_COLS];      // rows of every table
+    const int64_t *idx;                     // [R, ld] categorical values, column c at idx[r * ld + c]
+    int64_t ld;
+    int64_t R;
+    int32_t n_cols, d;
+    float *out;                             // forward [R, d]
+    const float *grad_out;                  // backward [R, d]
+    int32_t rows_per_cta;
+    int32_t *status;
+};
+
+// out[r, :] = sum_c tab_c[idx[r, c], :]
+template <int VEC>
+__global__ void __launch_bounds__(256) bag_fwd_kernel(const __grid_constant__ BagParams p) {
+    const int cpr = p.d / VEC;
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= p.R * cpr) return;
+    const int64_t r = t / cpr;
+    const int c0 = (int)(t % cpr) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    const int64_t *row = p.idx + r * p.ld;
+    for (int c = 0; c < p.n_cols; ++c) {
+        const int64_t v = __ldg(row + c);
+        if (v < 0 || v >= p.rows_of[c]) {           // nn.Embedding raises IndexError; here: status bit, row skipped
+            atomicOr(p.status, GSN_S_INDEX_RANGE);
+            continue;
+        }
+        const float *src = p.tab[c] + v * p.d + c0;
+        if (VEC == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
+            acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] += __ldg(src + i);
+        }
+    }
+    float *dst = p.out + r * p.d + c0;
+    if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dst[i] = acc[i];
+}
+
+// grad_tab_c[v, :] += sum_{r : idx[r, c] = v} grad_out[r, :].  One CTA = (block of rows, column c): the column's table
+// gradient is accumulated in shared memory (tables of categorical features are small) and flushed once with global
+// atomics; a table too large for shared memory takes the global atomics directly.
+__global__ void __launch_bounds__(256) bag_bwd_kernel(const __grid_constant__ BagParams p, int smem_floats) {
+    extern __shared__ float bag_acc[];
+    const int c = blockIdx.y;
+    const int V = p.rows_of[c], d = p.d;
+    const bool in_smem = (int64_t)V * d <= smem_floats;
+    float *gt = const_cast<float *>(p.tab[c]);
+    if (in_smem)
+        for (int i = threadIdx.x; i < V * d; i += 256) bag_acc[i] = 0.f;
+    __syncthreads();
+    const int64_t r0 = (int64_t)blockIdx.x * p.rows_per_cta;
+    const int64_t r1 = r0 + p.rows_per_cta < p.R ? r0 + p.rows_per_cta : p.R;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+        const int64_t v = __ldg(p.idx + r * p.ld + c);
+        if (v < 0 || v >= V) continue;
+        const float *g = p.grad_out + r * d;
+        float *dst = in_smem ? bag_acc + v * d : gt + v * d;
+        for (int j = lane; j < d; j += 32) atomicAdd(dst + j, __ldg(g + j));
+    }
+    if (!in_smem) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < V * d; i += 256) {
+        const float a = bag_acc[i];
+        if (a != 0.f) atomicAdd(gt + i, a);
+    }
+}
+
+struct OgbBwdParams {
+    const int32_t *rowptr, *eid, *nbr;      // edges grouped by SOURCE node j: eid = edge_index column, nbr = aggregation node i
+    int64_t N;
+    const float *x, *id, *ef, *eps, *g;
+    int32_t d, id_per_edge;
+    float *grad_x, *grad_ef;
+};
+
+// forward: out[i] = (1+eps) (x[i] [+ id[i]]) + sum_{e: j -> i} relu(x[j] + (id[j] | id[e]) + ef[e])
+// backward for node j:  grad_x[j] = (1+eps) g[j] + sum_{e: j -> i} [pre_e > 0] g[i]   ( = grad_id[j] for per-node ids)
+//                       grad_ef[e] = [pre_e > 0] g[i]                                  ( = grad_id[e] for per-edge ids)
+template <int VEC>
+__global__ void __launch_bounds__(256) ogb_bwd_kernel(const __grid_constant__ OgbBwdParams p) {
+    const int cpr = p.d / VEC;
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= p.N * cpr) return;
+    const int64_t j = t / cpr;
+    const int c0 = (int)(t % cpr) * VEC;
+    auto ld = [&](const float *ptr, float (&v)[VEC]) {
+        if (VEC == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(ptr));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) v[i] = __ldg(ptr + i);
+        }
+    };
+    auto st = [&](float *ptr, const float (&v)[VEC]) {
+        if (VEC == 4) *reinterpret_cast<float4 *>(ptr) = make_float4(v[0], v[1], v[2], v[3]);
+        else
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) ptr[i] = v[i];
+    };
+    float base[VEC], acc[VEC], gj[VEC];
+    ld(p.x + j * p.d + c0, base);
+    if (p.id && !p.id_per_edge) {
+        float idv[VEC];
+        ld(p.id + j * p.d + c0, idv);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) base[i] += idv[i];
+    }
+    ld(p.g + j * p.d + c0, gj);
+    const float one_eps = 1.0f + (p.eps ? __ldg(p.eps) : 0.0f);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = one_eps * gj[i];
+    const int kend = __ldg(p.rowptr + j + 1);
+    for (int k = __ldg(p.rowptr + j); k < kend; ++k) {
+        const int64_t e = __ldg(p.eid + k), i_node = __ldg(p.nbr + k);
+        float pre[VEC], gi[VEC], m[VEC];
+        ld(p.ef + e * p.d + c0, pre);
+        if (p.id && p.id_per_edge) {
+            float idv[VEC];
+            ld(p.id + e * p.d + c0, idv);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) pre[i] += idv[i];
+        }
+        ld(p.g + i_node * p.d + c0, gi);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            m[i] = (pre[i] + base[i] > 0.0f) ? gi[i] : 0.0f;
+            acc[i] += m[i];
+        }
+        st(p.grad_ef + e * p.d + c0, m);
+    }
+    st(p.grad_x + j * p.d + c0, acc);
+}
+
+inline bool tk_aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace gsn
+
+using namespace gsn;
+
+static int fill_bag(BagParams &p, const GsnBagCol *h_cols, int32_t n_cols, const int64_t *d_idx, int64_t ld, int64_t R, int32_t d,
+                    int32_t *d_status) {
+    if (!h_cols || n_cols < 1 || n_cols > GSN_MAX_BAG_COLS || !d_idx || R < 0 || d < 1 || ld < n_cols || !d_status) return GSN_E_INVALID;
+    for (int c = 0; c < n_cols; ++c) {
+        if (!h_cols[c].d_table || h_cols[c].rows < 1) return GSN_E_INVALID;
+        p.tab[c] = h_cols[c].d_table;
+        p.rows_of[c] = h_cols[c].rows;
+    }
+    p.idx = d_idx; p.ld = ld; p.R = R; p.n_cols = n_cols; p.d = d; p.status = d_status;
+    p.out = nullptr; p.grad_out = nullptr; p.rows_per_cta = 0;
+    return GSN_OK;
+}
+
+extern "C" int gsn_embedding_bag_fwd(const GsnBagCol *h_cols, int32_t n_cols, const int64_t *d_idx, int64_t ld, int64_t R, int32_t d,
+                                     float *d_out, int32_t *d_status, void *stream_) {
+    BagParams p;
+    int rc = fill_bag(p, h_cols, n_cols, d_idx, ld, R, d, d_status);
+    if (rc) return rc;
+    if (!d_out) return GSN_E_INVALID;
+    if (R == 0) return GSN_OK;
+    p.out = d_out;
+    bool v4 = d % 4 == 0 && tk_aligned16(d_out);
+    for (int c = 0; c < n_cols; ++c) v4 = v4 && tk_aligned16(h_cols[c].d_table);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (v4) bag_fwd_kernel<4><<<(unsigned)ceil_div(R * (d / 4), 256), 256, 0, stream>>>(p);
+    else bag_fwd_kernel<1><<<(unsigned)ceil_div(R * (int64_t)d, 256), 256, 0, stream>>>(p);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_embedding_bag_fwd");
+    return GSN_OK;
+}
+
+extern "C" int gsn_embedding_bag_bwd(const GsnBagCol *h_grad_cols, int32_t n_cols, const int64_t *d_idx, int64_t ld, int64_t R,
+                                     int32_t d, const float *d_grad_out, int32_t *d_status, void *stream_) {
+    BagParams p;
+    int rc = fill_bag(p, h_grad_cols, n_cols, d_idx, ld, R, d, d_status);
+    if (rc) return rc;
+    if (!d_grad_out) return GSN_E_INVALID;
+    if (R == 0) return GSN_OK;
+    p.grad_out = d_grad_out;
+    int vmax = 1;
+    for (int c = 0; c < n_cols; ++c) vmax = h_grad_cols[c].rows > vmax ? h_grad_cols[c].rows : vmax;
+    const int64_t cap = 96 * 1024 / 4;                       // floats of shared memory a CTA may use for one table
+    const int smem_floats = (int)((int64_t)vmax * d <= cap ? (int64_t)vmax * d : 0);
+    // enough CTAs to fill the machine, each amortising its flush over >= 256 rows
+    int64_t blocks = ceil_div((int64_t)kNumSMs * 2, n_cols);
+    if (blocks < 1) blocks = 1;
+    int64_t rows_per = ceil_div(R, blocks);
+    if (rows_per < 256) rows_per = 256;
+    p.rows_per_cta = (int32_t)rows_per;
+    const size_t smem = sizeof(float) * (size_t)smem_floats;
+    GSN_CUDA_OK(cudaFuncSetAttribute(bag_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    dim3 grid((unsigned)ceil_div(R, rows_per), (unsigned)n_cols);
+    bag_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(p, smem_floats);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_embedding_bag_bwd");
+    return GSN_OK;
+}
+
+extern "C" int gsn_mp_ogb_bwd(const int32_t *d_rowptr_src, const int32_t *d_eid_src, const int32_t *d_nbr_src, int64_t N, int64_t E,
+                              const float *d_x, const float *d_id, int32_t id_per_edge, const float *d_ef, int32_t d,
+                              const float *d_eps, const float *d_grad_out, float *d_grad_x, float *d_grad_ef, void *stream_) {
+    if (N < 0 || E < 0 || d < 1 || !d_rowptr_src || !d_x || !d_grad_out || !d_grad_x || (E > 0 && (!d_ef || !d_grad_ef || !d_eid_src || !d_nbr_src)))
+        return GSN_E_INVALID;
+    if (N == 0) return GSN_OK;
+    OgbBwdParams p{d_rowptr_src, d_eid_src, d_nbr_src, N, d_x, d_id, d_ef, d_eps, d_grad_out, d, id_per_edge, d_grad_x, d_grad_ef};
+    const bool v4 = d % 4 == 0 && tk_aligned16(d_x) && tk_aligned16(d_id) && tk_aligned16(d_ef) && tk_aligned16(d_grad_out) &&
+                    tk_aligned16(d_grad_x) && tk_aligned16(d_grad_ef);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (v4) ogb_bwd_kernel<4><<<(unsigned)ceil_div(N * (d / 4), 256), 256, 0, stream>>>(p);
+    else ogb_bwd_kernel<1><<<(unsigned)ceil_div(N * (int64_t)d, 256), 256, 0, stream>>>(p);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("gsn_mp_ogb_bwd");
+    return GSN_OK;
+}

@@ -81,17 +81,22 @@ def shard_batch(batch: Dict[str, np.ndarray], world: int, rank: int, balance: st
 def allreduce_gradients(parameters, group=None, average: bool = True):
     """Sum (average) the gradients of all ranks through ONE flat fp32 buffer: the model has ~0.4 M (ZINC) to
     3.3 M (molhiv) parameters, so a single latency-bound all-reduce beats per-tensor calls."""
-    params = [p for p in parameters if p.grad is not None]
+    # every trainable parameter takes part, a missing gradient (an unused parameter, an empty shard) as zeros: the
+    # buffer layout must be identical on every rank or the collective hangs / mixes tensors up
+    params = [p for p in parameters if p.requires_grad]
     if not params or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    flat = torch.cat([p.grad.reshape(-1).float() for p in params])
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
     off = 0
     for p in params:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
 
 
@@ -99,8 +104,11 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
     """replicate the weights of rank `src` (start of training)"""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src=src, group=group)
+    # in place on the tensors themselves (not .data): the version counters move, so weight-derived caches
+    # (ops.split_weight, FusedForward, mlp.bn_affine) see the new values
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src, group=group)
 
 
 def global_unique_per_column(local_ids: torch.Tensor, group=None) -> List[torch.Tensor]:

@@ -43,6 +43,10 @@ class _OgbSumEmbedding(nn.Module):
 
     def forward(self, x):
         embs = getattr(self, self._list_name)
+        from . import ops
+        tables = [embs[i].weight for i in range(x.shape[1])]
+        if ops.embedding_bag_ok(x, tables):
+            return ops.embedding_bag(x, tables)          # one launch (and one for the backward) instead of one per column
         out = 0
         for i in range(x.shape[1]):
             out = out + embs[i](x[:, i])
@@ -109,6 +113,11 @@ class multi_embedding(nn.Module):
         self.encoder = nn.ModuleList(tables)
 
     def forward(self, tensor):
+        if self.aggr == 'sum':
+            from . import ops
+            tables = [self.encoder[i].weight for i in range(tensor.shape[1])]
+            if ops.embedding_bag_ok(tensor, tables):
+                return ops.embedding_bag(tensor, tables)
         parts = [self.encoder[i](tensor[:, i]) for i in range(tensor.shape[1])]
         if self.aggr == 'concat':
             return torch.cat(parts, 1)

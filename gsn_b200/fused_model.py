@@ -222,7 +222,11 @@ class FusedModel(FusedForward):
         fm.n_layers, fm.D, fm.n_mats = len(self.layers), D, self.n_mats
         gpu = self.graphs_per_unit
         if gpu is None:
-            gpu = max(1, -(-G // (2 * 148)))
+            # a tile costs about the same whether it holds 20 rows or 128 (its phases are latency-bound), so tiles are
+            # filled: ~100 rows' worth of graphs per unit (one tile, rarely two) for small batches -- a step then occupies
+            # few SMs and steps of other streams run beside it -- and >= 2 units per SM for large ones
+            avg = max(1.0, N / max(G, 1))
+            gpu = max(1, int(100.0 / avg), -(-G // (2 * 148)))
         fm.graphs_per_unit = int(gpu)
         fm.Whi, fm.Wlo = self.Whi.data_ptr(), self.Wlo.data_ptr()
         fm.rowptr, fm.nbr, fm.node_ptr = plan.rowptr.data_ptr(), plan.nbr.data_ptr(), node_ptr.data_ptr()

@@ -16,11 +16,21 @@ import torch
 from .. import ops
 
 
+FUSED_OGB = True        # 'ogb' message kind: fused forward + fused backward (gsn_mp_ogb_fwd / gsn_mp_ogb_bwd)
+PURE_TORCH = False      # measurement aid (scripts/bench_ogb.py --impl eager_torch): the reference's formulation op by op
+#                         in eager PyTorch (index_select gathers, index_add_ scatter) -- the incumbent on the same GPU
+
+
 def segment_sum(msgs, plan):
+    if PURE_TORCH:
+        out = torch.zeros((plan.N, msgs.shape[1]), dtype=msgs.dtype, device=msgs.device)
+        return out.index_add_(0, plan.edge_index[plan.select], msgs)
     return ops.segment_sum_ad(plan, msgs)
 
 
 def gather_rows(x, edge_index, row):
+    if PURE_TORCH:
+        return x.index_select(0, edge_index[row])
     return ops.gather_rows_ad(x, edge_index, row)
 
 
@@ -47,6 +57,12 @@ def forward_with_grad(layer, x, edge_index, identifiers, ef):
             msg_parts.append(ef_nb)
         agg = segment_sum(torch.cat(msg_parts, -1).float(), plan)
         return layer.update_fn((1 + layer.eps) * torch.cat(self_parts, -1) + agg)
+    if (layer.msg_kind == 'ogb' and FUSED_OGB and not PURE_TORCH and x.is_cuda and not layer.eps.requires_grad
+            and ef is not None):
+        # fused forward + fused backward (relu mask recomputed): gsn_mp_ogb_fwd / gsn_mp_ogb_bwd
+        agg = ops.ogb_aggregate_ad(edge_index, n, layer.flow, x, identifiers if layer.uses_ids else None, local, ef.float(),
+                                   layer.eps)
+        return layer.update_fn(agg)
     if layer.msg_kind == 'ogb':
         self_msg = x
         m = x_j

@@ -226,24 +226,28 @@ def _dp(t):
 # Tensor-core dense tail (tcgen05 3xTF32).  "auto": use it whenever the shapes allow (K % 4 == 0, aligned).
 TENSOR_CORES = 'auto'       # 'auto' | 'off'
 FORCE_PRESPLIT = False       # testing aid (see gsn_tc_force_presplit)
-_wsplit_cache = {}
+import weakref
+
+_wsplit_cache = {}          # id(tensor) -> (weakref to the tensor, stamp, hi, lo); evicted when the tensor dies
 
 
 def split_weight(W: torch.Tensor):
-    """(W_hi, W_lo) tf32 split of a weight matrix, cached per (storage, version)"""
-    key = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0))
+    """(W_hi, W_lo) tf32 split of a weight matrix, cached ON the tensor object: an entry is valid for the same Python
+    tensor with the same storage address and version only.  (Keying on data_ptr alone is wrong: nn.Module.cpu() / .cuda()
+    swap a Parameter's storage in place, the freed address is recycled by another layer's weight of the same shape and
+    version, and the stale split of the OLD weight would be returned.)"""
+    stamp = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0))
+    key = id(W)
     hit = _wsplit_cache.get(key)
-    if hit is None:
+    if hit is None or hit[0]() is not W or hit[1] != stamp:
         hi = torch.empty((W.shape[0], W.shape[1]), dtype=torch.float32, device=W.device)
         lo = torch.empty_like(hi)
         with torch.cuda.device(W.device):
             _lib.call('split_tf32', 'gsn_split_tf32', _lib.ptr(W), W.shape[0], W.shape[1], W.stride(0), _lib.ptr(hi),
                       _lib.ptr(lo), _lib.stream_ptr())
-        if len(_wsplit_cache) > 256:
-            _wsplit_cache.clear()
-        hit = (hi, lo, W)           # keep W alive so the data_ptr key cannot be recycled
+        hit = (weakref.ref(W, lambda _r, k=key: _wsplit_cache.pop(k, None)), stamp, hi, lo)
         _wsplit_cache[key] = hit
-    return hit[0], hit[1]
+    return hit[2], hit[3]
 
 
 def _tc_eligible(A1, A2, W):
@@ -402,3 +406,109 @@ def gather_rows_ad(x: torch.Tensor, edge_index: torch.Tensor, row: int) -> torch
     if torch.is_grad_enabled() and x.requires_grad:
         return _GatherRowsFn.apply(x, edge_index, row, x.shape[0])
     return x.index_select(0, edge_index[row])
+
+
+# ----------------------------------------------------------------------------
+# training-step operators (ogbg-molhiv recipe): fused ogb message with its own backward, embedding bag
+# ----------------------------------------------------------------------------
+class _OgbAggregateFn(torch.autograd.Function):
+    """(1+eps)*(x [+ id]) + sum_e relu(x_j + id + e_ij)  (GSN_edge_sparse_ogb.py:75-84,119-126) with the fused forward
+    kernel and a fused backward that recomputes the relu mask: no [E, d] tensor is saved"""
+
+    @staticmethod
+    def forward(ctx, x, identifiers, ef, eps, plan, plan_src, id_per_edge):
+        ctx.plan_src, ctx.id_per_edge = plan_src, bool(id_per_edge)
+        x, ef = _f32c(x, 'x'), _f32c(ef, 'edge_features')
+        idt = _f32c(identifiers, 'identifiers')
+        ctx.save_for_backward(x, idt if idt is not None else x.new_empty(0), ef, eps)
+        ctx.has_id = idt is not None
+        return ogb_aggregate(plan, x, idt, id_per_edge, ef, eps)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, idt, ef, eps = ctx.saved_tensors
+        idt = idt if ctx.has_id else None
+        p = ctx.plan_src
+        g = _f32c(grad_out, 'grad_out')
+        d = x.shape[1]
+        grad_x = torch.empty_like(x)
+        grad_ef = torch.empty_like(ef)
+        with torch.cuda.device(x.device):
+            _lib.call('mp_ogb_bwd', 'gsn_mp_ogb_bwd', _lib.ptr(p.rowptr), _lib.ptr(p.eid), _lib.ptr(p.nbr), p.N, p.E, _lib.ptr(x),
+                      _lib.ptr(idt), int(ctx.id_per_edge), _lib.ptr(ef), d, _lib.ptr(eps), _lib.ptr(g), _lib.ptr(grad_x),
+                      _lib.ptr(grad_ef), _lib.stream_ptr())
+        grad_id = None
+        if idt is not None:
+            grad_id = grad_ef if ctx.id_per_edge else grad_x
+        return grad_x, grad_id, grad_ef, None, None, None, None
+
+
+def ogb_aggregate_ad(edge_index, num_nodes, flow, x, identifiers, id_per_edge, ef, eps):
+    """differentiable ogb message (w.r.t. x, identifiers, edge features; eps must not require grad)"""
+    plan = edge_plan(edge_index, num_nodes, flow)
+    plan_src = edge_plan(edge_index, num_nodes, 'target_to_source' if plan.select == 1 else 'source_to_target')
+    return _OgbAggregateFn.apply(x, identifiers, ef, eps, plan, plan_src, id_per_edge)
+
+
+class GsnBagCol(ctypes.Structure):
+    """ctypes image of `struct GsnBagCol`."""
+    _fields_ = [('table', ctypes.c_void_p), ('rows', ctypes.c_int32), ('_pad', ctypes.c_int32)]
+
+
+MAX_BAG_COLS = 96
+_bag_status = {}
+
+
+def _bag_cols(tables):
+    cols = (GsnBagCol * len(tables))()
+    for i, t in enumerate(tables):
+        cols[i].table, cols[i].rows = t.data_ptr(), int(t.shape[0])
+    return cols
+
+
+def _bag_status_word(dev):
+    st = _bag_status.get(dev)
+    if st is None:
+        st = _bag_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return st
+
+
+class _EmbeddingBagFn(torch.autograd.Function):
+    """sum_c table_c[idx[:, c]] (multi_embedding aggr 'sum', AtomEncoder, BondEncoder) in one launch each way"""
+
+    @staticmethod
+    def forward(ctx, idx, *tables):
+        ctx.save_for_backward(idx)
+        ctx.shapes = [tuple(t.shape) for t in tables]
+        ws = [_f32c(t.detach(), 'embedding table') for t in tables]
+        R, d = int(idx.shape[0]), int(ws[0].shape[1])
+        out = torch.empty((R, d), dtype=torch.float32, device=idx.device)
+        with torch.cuda.device(idx.device):
+            _lib.call('embedding_bag', 'gsn_embedding_bag_fwd', ctypes.cast(_bag_cols(ws), ctypes.c_void_p), len(ws), _lib.ptr(idx),
+                      idx.stride(0), R, d, _lib.ptr(out), _lib.ptr(_bag_status_word(idx.device)), _lib.stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        g = _f32c(grad_out, 'grad_out')
+        grads = [torch.zeros(s, dtype=torch.float32, device=g.device) for s in ctx.shapes]
+        R, d = int(idx.shape[0]), int(g.shape[1])
+        with torch.cuda.device(g.device):
+            _lib.call('embedding_bag_bwd', 'gsn_embedding_bag_bwd', ctypes.cast(_bag_cols(grads), ctypes.c_void_p), len(grads),
+                      _lib.ptr(idx), idx.stride(0), R, d, _lib.ptr(g), _lib.ptr(_bag_status_word(g.device)), _lib.stream_ptr())
+        return (None,) + tuple(grads)
+
+
+EMBEDDING_BAG = True        # False: per-column nn.Embedding lookups (measurement aid, see graph_filters/autograd.py)
+
+
+def embedding_bag_ok(idx, tables) -> bool:
+    return (EMBEDDING_BAG and idx.is_cuda and idx.dtype == torch.int64 and idx.dim() == 2 and idx.stride(1) == 1 and 1 <= len(tables) <= MAX_BAG_COLS
+            and idx.shape[1] == len(tables) and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                                                    and t.shape[1] == tables[0].shape[1] for t in tables))
+
+
+def embedding_bag(idx, tables):
+    """idx int64 [R, C] (row stride arbitrary), tables: C weight matrices [rows_c, d] -> fp32 [R, d]"""
+    return _EmbeddingBagFn.apply(idx, *tables)

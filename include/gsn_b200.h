@@ -328,6 +328,37 @@ int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_t *d_eid, c
  * d_perm = d_eid), which removes one dependent load per edge; 0: indexed by edge_index column. */
 
 /* ------------------------------------------------------------------ */
+/* training step (ogbg-molhiv recipe)                                  */
+/* ------------------------------------------------------------------ */
+/*
+ * Embedding bag over categorical columns: out[r,:] = sum_c table_c[idx[r*ld + c], :]  -- multi_embedding with aggr 'sum'
+ * (utils_graph_learning.py:134-167) and ogb's AtomEncoder / BondEncoder in one launch; backward adds
+ * sum_{r: idx[r,c]=v} grad_out[r,:] into grad_table_c[v,:] (caller zero-initialises the gradient tables; accumulation
+ * order is not fixed, like torch's embedding backward).  Values outside a table set GSN_S_INDEX_RANGE (nn.Embedding
+ * raises IndexError) and are skipped.
+ */
+#define GSN_MAX_BAG_COLS 96
+typedef struct GsnBagCol {
+    const float *d_table;   /* [rows, d] fp32 (forward: weights; backward: gradient of the weights) */
+    int32_t rows, _pad;
+} GsnBagCol;
+int gsn_embedding_bag_fwd(const GsnBagCol *h_cols, int32_t n_cols, const int64_t *d_idx, int64_t ld, int64_t R, int32_t d,
+                          float *d_out, int32_t *d_status, void *stream);
+int gsn_embedding_bag_bwd(const GsnBagCol *h_grad_cols, int32_t n_cols, const int64_t *d_idx, int64_t ld, int64_t R, int32_t d,
+                          const float *d_grad_out, int32_t *d_status, void *stream);
+
+/*
+ * Backward of gsn_mp_ogb_fwd (autograd through GSN_edge_sparse_ogb.py:86-129) w.r.t. x, identifiers and edge features.
+ * The CSR is the TRANSPOSED grouping (gsn_csr_build keyed by the gathered endpoint j; nbr = aggregation node i):
+ *   grad_x[j]  = (1+eps) g[j] + sum_{e: j->i} [x[j] + id + ef[e] > 0] g[i]     (also the gradient of per-node identifiers)
+ *   grad_ef[e] = [x[j] + id + ef[e] > 0] g[i]                                  (also the gradient of per-edge identifiers)
+ * Nothing of size [E, d] has to be saved by the forward: the relu mask is recomputed from the layer inputs.
+ */
+int gsn_mp_ogb_bwd(const int32_t *d_rowptr_src, const int32_t *d_eid_src, const int32_t *d_nbr_src, int64_t N, int64_t E,
+                   const float *d_x, const float *d_id, int32_t id_per_edge, const float *d_ef, int32_t d, const float *d_eps,
+                   const float *d_grad_out, float *d_grad_x, float *d_grad_ef, void *stream);
+
+/* ------------------------------------------------------------------ */
 /* whole-model fused forward                                           */
 /* ------------------------------------------------------------------ */
 /*

@@ -7,7 +7,13 @@ B = 512 synthetic molhiv-shaped graphs: COUNT time and one TRAINING step (forwar
                                                    # N GPUs: every rank trains on its own B graphs (weak scaling), weights
                                                    # broadcast from rank 0, ONE flat-buffer NCCL all-reduce of the gradients
                                                    # per step (the only collective of the system; BatchNorm stays per shard)
+    python scripts/bench_ogb.py --impl eager_torch # the reference's formulation op by op in eager PyTorch on the same GPU
+                                                   # (index_select gathers, relu, index_add_ scatter, one nn.Embedding per
+                                                   # column, cuBLAS MLPs, no CUDA graph): the incumbent on the box
     python scripts/bench_ogb.py --impl reference   # the unmodified reference model on the host CPU (needs /root/reference)
+
+ours: fused ogb message forward + backward kernels, embedding-bag kernels for the 72 identifier columns / atom / bond
+encoders, and the whole step (forward + BCE + backward [+ all-reduce] + Adam) replayed from CUDA graphs (--no-graph: eager).
 """
 import argparse
 import contextlib
@@ -47,6 +53,21 @@ def model_args(L, d, dh, dropout):
                 d_out_id_embedding=d, d_out_degree_embedding=d, extend_dims=True, activation='relu')
 
 
+def _clocks(index):
+    """one nvidia-smi sample right after the timed region (B200_PROFILING.md clocks line)"""
+    import subprocess
+    q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    try:
+        out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().split(',')
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        return {'sm_mhz': float(out[0]), 'sm_max_mhz': float(out[1]),
+                'reasons': [n for n, v in zip(names, out[2:]) if 'Active' in v and 'Not' not in v]}
+    except Exception as ex:
+        return {'error': repr(ex)[:100]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--impl', default='ours')
@@ -54,10 +75,12 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--id-cap', type=int, default=64, help='identifier embedding rows per column (counts are clamped)')
+    ap.add_argument('--no-graph', action='store_true', help='eager training step (no CUDA graph)')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
-    if world > 1 and a.impl == 'ours':
+    gpu_impl = a.impl in ('ours', 'eager_torch')
+    if world > 1 and gpu_impl:
         os.environ.setdefault('NCCL_DEBUG', 'WARN')
         torch.cuda.set_device(local)
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
@@ -79,8 +102,11 @@ def main():
     class Obj:
         pass
 
-    if a.impl == 'ours':
-        from gsn_b200 import counting, patterns
+    if gpu_impl:
+        from gsn_b200 import counting, ops, patterns
+        from gsn_b200.graph_filters import autograd as gf_autograd
+        if a.impl == 'eager_torch':
+            gf_autograd.PURE_TORCH, ops.EMBEDDING_BAG = True, False
         from gsn_b200.network import GNN_OGB
         dev = torch.device('cuda', local)
         torch.cuda.set_device(dev)
@@ -108,26 +134,76 @@ def main():
         data = Obj()
         data.edge_index, data.batch, data.x, data.edge_features = ei_d, torch.from_numpy(b['batch']).to(dev), x.to(dev), ef.to(dev)
         data.identifiers, data.degrees, data.node_ptr = ids, torch.from_numpy(b['degrees']).to(dev), node_ptr.to(dev)
+        data.num_graphs = a.batch
         yd = y.to(dev)
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        use_graph = a.impl == 'ours' and not a.no_graph
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph)
         if world > 1:
             from gsn_b200 import distributed as gd
             gd.broadcast_parameters(model, src=0)
         params = [p_ for p_ in model.parameters()]
+        from gsn_b200 import _lib
 
-        def step():
+        def fwd_bwd():
             opt.zero_grad(set_to_none=True)
             loss = torch.nn.functional.binary_cross_entropy_with_logits(model(data), yd)
             loss.backward()
+            return loss
+
+        def step():
+            loss = fwd_bwd()
             if world > 1:
                 gd.allreduce_gradients(params)          # one flat fp32 buffer, averaged
             opt.step()
             return loss
-        for _ in range(a.warmup):
+        ar_ms = None
+        if use_graph:
+            # whole step from CUDA graphs: forward + loss + backward in one graph, Adam (capturable) in a second one;
+            # between them (N > 1 only) the one collective of the system, an NCCL all-reduce of the flat gradient buffer
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(3, a.warmup)):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count()
+            g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g_fb):
+                static_loss = fwd_bwd()
+            own_launches = _lib.launch_count() - l0
+            with torch.cuda.graph(g_opt):
+                opt.step()
+
+            def step():                                  # noqa: F811
+                g_fb.replay()
+                if world > 1:
+                    gd.allreduce_gradients(params)
+                g_opt.replay()
+                return static_loss
+            for _ in range(a.warmup):
+                step()
+            torch.cuda.synchronize()
+            if world > 1:                                # the all-reduce alone, device time
+                e0, e1 = ev(), ev()
+                e0.record()
+                for _ in range(a.steps):
+                    gd.allreduce_gradients(params)
+                e1.record()
+                torch.cuda.synchronize()
+                ar_ms = e0.elapsed_time(e1) / a.steps
+        else:
+            for _ in range(a.warmup):
+                step()
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count()
             step()
+            own_launches = _lib.launch_count() - l0
+            torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
         torch.cuda.synchronize()
-        from gsn_b200 import _lib
-        l0 = _lib.launch_count()
         e0, e1 = ev(), ev()
         e0.record()
         for _ in range(a.steps):
@@ -139,9 +215,12 @@ def main():
             tt = torch.tensor([ms], dtype=torch.float64, device=dev)
             torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
             ms = float(tt[0])
+        n_par = sum(p_.numel() for p_ in params)
         res.update(n_gpus=world, train_step_ms=ms, graphs_per_s=world * a.batch / (ms * 1e-3), loss=float(loss),
-                   gsn_kernel_launches_per_step=(_lib.launch_count() - l0) / a.steps,
-                   count_plus_step_graphs_per_s=world * a.batch / ((ms + res['count_ms']) * 1e-3))
+                   cuda_graph=bool(use_graph), gsn_kernel_launches_per_step=own_launches,
+                   parameters=n_par, allreduce_bytes=4 * n_par if world > 1 else 0, allreduce_ms=ar_ms,
+                   count_plus_step_graphs_per_s=world * a.batch / ((ms + res['count_ms']) * 1e-3),
+                   clocks=_clocks(local))
         model.eval()
         with torch.no_grad():
             for _ in range(2):
@@ -181,7 +260,7 @@ def main():
                         'threads = cores; identifiers random (graph-tool absent, COUNT not timed)')
     if rank == 0:
         print(json.dumps(res))
-    if world > 1 and a.impl == 'ours':
+    if world > 1 and gpu_impl:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
