@@ -509,7 +509,7 @@ extern "C" int gsn_count_small(const int64_t *d_edge_index, int64_t E, const int
     int64_t T = (int64_t)(768.0 / (avg_deg > 1.0 ? avg_deg : 1.0));
     const int64_t t_fill = N / (kNumSMs * 4);
     if (T > t_fill) T = t_fill;
-    if (T < 16) T = 16;
+    if (T < 48) T = 48;              // >= ~2 molecules per CTA: a chunk pays its set-up (searches, scan) once
     if (T > 1024) T = 1024;
     const bool small_batch = ceil_div(N, T) <= 2 * kNumSMs;
     const int NT = small_batch ? 128 : 256;

@@ -58,33 +58,50 @@ __global__ void __launch_bounds__(256) bag_fwd_kernel(const __grid_constant__ Ba
         for (int i = 0; i < VEC; ++i) dst[i] = acc[i];
 }
 
-// grad_tab_c[v, :] += sum_{r : idx[r, c] = v} grad_out[r, :].  One CTA = (block of rows, column c): the column's table
-// gradient is accumulated in shared memory (tables of categorical features are small) and flushed once with global
-// atomics; a table too large for shared memory takes the global atomics directly.
-__global__ void __launch_bounds__(256) bag_bwd_kernel(const __grid_constant__ BagParams p, int smem_floats) {
-    extern __shared__ float bag_acc[];
+// grad_tab_c[v, :] += sum_{r : idx[r, c] = v} grad_out[r, :].  One CTA = (block of rows, column c).  The column's values of
+// the block are staged in shared memory; every warp then owns table rows v = warp, warp + 8, ...: it finds the block's
+// rows holding v with ballots over the staged values and sums their gradient rows in REGISTERS (lanes across d), so the
+// only atomics are one global fp32 add per (table row present in the block, channel) -- no shared-memory atomics, whose
+// fp32 form is a compare-and-swap loop that serialises on the few distinct values of a categorical column.
+constexpr int kBagRows = 1024;          // rows per CTA
+constexpr int kBagMaxD = 1024;          // channels a lane can hold (32 per lane)
+template <int PER>          // channels per lane: d <= 32 * PER
+__global__ void __launch_bounds__(256) bag_bwd_kernel(const __grid_constant__ BagParams p) {
+    __shared__ int32_t vals[kBagRows];
     const int c = blockIdx.y;
     const int V = p.rows_of[c], d = p.d;
-    const bool in_smem = (int64_t)V * d <= smem_floats;
     float *gt = const_cast<float *>(p.tab[c]);
-    if (in_smem)
-        for (int i = threadIdx.x; i < V * d; i += 256) bag_acc[i] = 0.f;
-    __syncthreads();
-    const int64_t r0 = (int64_t)blockIdx.x * p.rows_per_cta;
-    const int64_t r1 = r0 + p.rows_per_cta < p.R ? r0 + p.rows_per_cta : p.R;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t r = r0 + warp; r < r1; r += 8) {
-        const int64_t v = __ldg(p.idx + r * p.ld + c);
-        if (v < 0 || v >= V) continue;
-        const float *g = p.grad_out + r * d;
-        float *dst = in_smem ? bag_acc + v * d : gt + v * d;
-        for (int j = lane; j < d; j += 32) atomicAdd(dst + j, __ldg(g + j));
+    const int64_t r0 = (int64_t)blockIdx.x * kBagRows;
+    const int n = (int)((r0 + kBagRows < p.R ? r0 + kBagRows : p.R) - r0);
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int64_t v = __ldg(p.idx + (r0 + i) * p.ld + c);
+        vals[i] = (v >= 0 && v < V) ? (int32_t)v : -1;           // out of range: flagged by the forward, skipped here
     }
-    if (!in_smem) return;
     __syncthreads();
-    for (int i = threadIdx.x; i < V * d; i += 256) {
-        const float a = bag_acc[i];
-        if (a != 0.f) atomicAdd(gt + i, a);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int v = warp; v < V; v += 8) {
+        float acc[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) acc[j] = 0.f;
+        bool any = false;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            unsigned m = __ballot_sync(0xffffffffu, i < n && vals[i] == v);
+            while (m) {
+                const int b = __ffs((int)m) - 1;
+                m &= m - 1;
+                any = true;
+                const float *g = p.grad_out + (r0 + base + b) * d;
+#pragma unroll
+                for (int j = 0; j < PER; ++j)
+                    if (lane + 32 * j < d) acc[j] += __ldg(g + lane + 32 * j);
+            }
+        }
+        if (any) {
+#pragma unroll
+            for (int j = 0; j < PER; ++j)
+                if (lane + 32 * j < d) atomicAdd(gt + (int64_t)v * d + lane + 32 * j, acc[j]);
+        }
     }
 }
 
@@ -200,20 +217,12 @@ extern "C" int gsn_embedding_bag_bwd(const GsnBagCol *h_grad_cols, int32_t n_col
     if (!d_grad_out) return GSN_E_INVALID;
     if (R == 0) return GSN_OK;
     p.grad_out = d_grad_out;
-    int vmax = 1;
-    for (int c = 0; c < n_cols; ++c) vmax = h_grad_cols[c].rows > vmax ? h_grad_cols[c].rows : vmax;
-    const int64_t cap = 96 * 1024 / 4;                       // floats of shared memory a CTA may use for one table
-    const int smem_floats = (int)((int64_t)vmax * d <= cap ? (int64_t)vmax * d : 0);
-    // enough CTAs to fill the machine, each amortising its flush over >= 256 rows
-    int64_t blocks = ceil_div((int64_t)kNumSMs * 2, n_cols);
-    if (blocks < 1) blocks = 1;
-    int64_t rows_per = ceil_div(R, blocks);
-    if (rows_per < 256) rows_per = 256;
-    p.rows_per_cta = (int32_t)rows_per;
-    const size_t smem = sizeof(float) * (size_t)smem_floats;
-    GSN_CUDA_OK(cudaFuncSetAttribute(bag_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    dim3 grid((unsigned)ceil_div(R, rows_per), (unsigned)n_cols);
-    bag_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(p, smem_floats);
+    if (d > kBagMaxD) return GSN_E_UNSUPPORTED;
+    dim3 grid((unsigned)ceil_div(R, kBagRows), (unsigned)n_cols);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (d <= 128) bag_bwd_kernel<4><<<grid, 256, 0, stream>>>(p);
+    else if (d <= 512) bag_bwd_kernel<16><<<grid, 256, 0, stream>>>(p);
+    else bag_bwd_kernel<32><<<grid, 256, 0, stream>>>(p);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_embedding_bag_bwd");
     return GSN_OK;

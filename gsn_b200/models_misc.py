@@ -46,10 +46,17 @@ class mlp(nn.Module):
 
     def hidden(self, x, i):
         """activation(bn_i(fc_i(x)))"""
-        x = self.fc[i](x)
+        x = self._fc(i, x)
         if self.batch_norm:
             x = self.bn[i](x)
         return self.activation(x)
+
+    def _fc(self, i, x):
+        """Linear i on the autograd path: forward + input gradient on the library's tensor-core kernel for CUDA rows"""
+        if x.is_cuda and x.dim() == 2:
+            from . import ops
+            return ops.linear_ad(x, self.fc[i].weight, self.fc[i].bias)
+        return self.fc[i](x)
 
     def _own_kernels(self, x) -> bool:
         """eval / no-grad forward on a CUDA tensor: nothing to differentiate, BatchNorm is a fixed affine"""
@@ -76,7 +83,7 @@ class mlp(nn.Module):
             x = torch.cat((x, x2), -1)
         for i in range(len(self.fc) - 1):
             x = self.hidden(x, i)
-        return self.fc[-1](x)
+        return self._fc(len(self.fc) - 1, x)
 
     def bn_affine(self, i, batch_stats=None):
         """BatchNorm i as per-channel (scale, shift): y = h*scale + shift.

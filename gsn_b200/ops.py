@@ -512,3 +512,39 @@ def embedding_bag_ok(idx, tables) -> bool:
 def embedding_bag(idx, tables):
     """idx int64 [R, C] (row stride arbitrary), tables: C weight matrices [rows_c, d] -> fp32 [R, d]"""
     return _EmbeddingBagFn.apply(idx, *tables)
+
+
+class _TcLinearFn(torch.autograd.Function):
+    """y = x W^T + b with the forward and the input gradient on the tcgen05 3xTF32 kernel (both are row-parallel GEMMs
+    over the N or E rows); the weight gradient g^T x reduces over those rows and stays a library SGEMM (fp32)"""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return linear(x, W, bias=b)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        g = _f32c(g, 'grad_out')
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            Wt = W.detach().t().contiguous()               # [in, out]: dX = g W  ==  linear(g, weight = W^T)
+            gx = linear(g, Wt) if _tc_eligible(g, None, Wt) else g @ W
+        if ctx.needs_input_grad[1]:
+            gw = g.t() @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb
+
+
+TC_TRAINING = True          # False: nn.Linear (cuBLAS fp32 SGEMM) in the training path
+
+
+def linear_ad(x, W, b):
+    """differentiable Linear: tensor-core forward / input gradient when the shapes allow, else torch"""
+    if (TC_TRAINING and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] >= 128
+            and _tc_eligible(x if x.is_contiguous() else x.contiguous(), None, W)):
+        return _TcLinearFn.apply(x.contiguous(), W, b)
+    return torch.nn.functional.linear(x, W, b)

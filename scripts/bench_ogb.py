@@ -76,6 +76,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--id-cap', type=int, default=64, help='identifier embedding rows per column (counts are clamped)')
     ap.add_argument('--no-graph', action='store_true', help='eager training step (no CUDA graph)')
+    ap.add_argument('--profile', action='store_true', help='torch.profiler table of the eager step (top kernels by device time)')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -106,7 +107,7 @@ def main():
         from gsn_b200 import counting, ops, patterns
         from gsn_b200.graph_filters import autograd as gf_autograd
         if a.impl == 'eager_torch':
-            gf_autograd.PURE_TORCH, ops.EMBEDDING_BAG = True, False
+            gf_autograd.PURE_TORCH, ops.EMBEDDING_BAG, ops.TC_TRAINING = True, False, False
         from gsn_b200.network import GNN_OGB
         dev = torch.device('cuda', local)
         torch.cuda.set_device(dev)
@@ -215,6 +216,13 @@ def main():
             tt = torch.tensor([ms], dtype=torch.float64, device=dev)
             torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
             ms = float(tt[0])
+        if a.profile and rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(3):
+                    loss = step()
+                torch.cuda.synchronize()
+            sys.stderr.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=90) + '\n')
         n_par = sum(p_.numel() for p_ in params)
         res.update(n_gpus=world, train_step_ms=ms, graphs_per_s=world * a.batch / (ms * 1e-3), loss=float(loss),
                    cuda_graph=bool(use_graph), gsn_kernel_launches_per_step=own_launches,
