@@ -46,8 +46,6 @@ _SIGNATURES = {
     'gsn_split_tf32': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'gsn_tc_linear_workspace_bytes': (ctypes.c_int, [_i64, _i32, _szp]),
     'gsn_tc_linear_fwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
-    'gsn_tc_debug_buffer': (ctypes.c_int, [_vp]),
-    'gsn_tc_force_presplit': (ctypes.c_int, [ctypes.c_int]),
     'gsn_embedding_bag_fwd': (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     'gsn_embedding_bag_bwd': (ctypes.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     'gsn_mp_ogb_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -235,11 +235,8 @@ __global__ void k_missing_check(const int32_t *__restrict__ rowptr, int64_t N, c
 
 template <int W>
 int launch_count(const CountParams &prm, int64_t chunks, size_t smem, cudaStream_t stream) {
-    static bool attr_set = false;   // benign race: the attribute is idempotent
-    if (!attr_set) {
-        GSN_CUDA_OK(cudaFuncSetAttribute(count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    // per launch (cheap): the attribute belongs to the current device
+    GSN_CUDA_OK(cudaFuncSetAttribute(count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     count_kernel<W><<<(unsigned)chunks, kCountThreads, smem, stream>>>(prm);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("count_kernel");

@@ -343,12 +343,8 @@ extern "C" int gsn_graph_build(const int64_t *d_edge_index, int64_t E, const int
 
     if (N > 0 && N <= kGraphSmallMaxN && (int64_t)N * W <= kGraphSmallMaxWords && E <= 65536) {
         const size_t smem = sizeof(uint64_t) * (size_t)N * W + sizeof(int32_t) * (size_t)(2 * N + 2);
-        static bool attr = false;
-        if (!attr) {
-            GSN_CUDA_OK(cudaFuncSetAttribute(graph_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(uint64_t) * kGraphSmallMaxWords + sizeof(int32_t) * (2 * kGraphSmallMaxN + 2))));
-            attr = true;
-        }
+        GSN_CUDA_OK(cudaFuncSetAttribute(graph_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(uint64_t) * kGraphSmallMaxWords + sizeof(int32_t) * (2 * kGraphSmallMaxN + 2))));
         graph_build_small_kernel<<<1, 1024, smem, stream>>>(src, dst, (int)E, d_node_ptr, (int)G, (int)N, W, nbase, adj, rowptr,
                                                             slot_src, slot_dst, slot_col, d_status);
         GSN_BUMP(1);

@@ -668,12 +668,8 @@ extern "C" int gsn_csr_build(const int64_t *d_key, const int64_t *d_other, int64
     int32_t *scan_tmp = (int32_t *)((char *)d_ws + 2 * seg);
     if (N <= kCsrSmallMaxN && E <= 8 * kCsrSmallMaxN) {
         const size_t smem = sizeof(int32_t) * (size_t)(2 * N + 2);
-        static bool attr = false;
-        if (!attr) {
-            GSN_CUDA_OK(cudaFuncSetAttribute(csr_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(int32_t) * (2 * kCsrSmallMaxN + 2))));
-            attr = true;
-        }
+        GSN_CUDA_OK(cudaFuncSetAttribute(csr_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(int32_t) * (2 * kCsrSmallMaxN + 2))));
         csr_build_small_kernel<<<1, 1024, smem, stream>>>(d_key, d_other, (int)E, (int)N, d_rowptr, d_eid, d_nbr, d_status);
         GSN_BUMP(1);
         GSN_LAUNCH_OK("gsn_csr_build");
@@ -868,7 +864,6 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool v4 = dh % 4 == 0 && aligned16(d_P) && aligned16(d_Q) && aligned16(d_S) && aligned16(d_Tn) && aligned16(d_Te);
     (void)te_rows;
-    static const bool no_tight = getenv("GSN_NO_TIGHT") != nullptr;      // A/B aid (scripts/p1_variants.py)
     const int cpr4 = dh / 4;
     const bool pow2 = v4 && (cpr4 & (cpr4 - 1)) == 0;
     int sh = 0;
@@ -876,7 +871,7 @@ extern "C" int gsn_mp_general_edge_idx_fwd(const int32_t *d_rowptr, const int32_
     // 32-bit element indexing: float4 offsets into P / Tn ([rows, 2dh]), S and the CSR-ordered edge rows
     const bool tight = pow2 && !d_scale && !d_shift && edge_rows_csr && N * 2 * cpr4 < (int64_t)1 << 31 &&
                        E * (int64_t)(n_edge_cols > 0 ? n_edge_cols : 1) < (int64_t)1 << 31 &&
-                       (int64_t)te_rows * cpr4 < (int64_t)1 << 31 && !no_tight;
+                       (int64_t)te_rows * cpr4 < (int64_t)1 << 31;
     if (tight && !d_Q && ((d_P && n_node_cols == 0 && n_edge_cols == 1) || (!d_P && n_node_cols == 1 && n_edge_cols >= 1))) {
         const uint32_t total = (uint32_t)(N * cpr4);
         const unsigned grid = (unsigned)ceil_div(total, kMpThreads);

@@ -28,8 +28,6 @@ struct TcEpilogue {
     const int32_t *tab_idx;
     float *C;
     int M, Nout, K, ldc, tab_ld, act, accumulate;
-    long long *dbg;          // optional [grid, 8] clock64 stamps (profiling aid)
-    int mode;                // experiment switches (GSN_TC_MODE): 1 skip epilogue, 2 skip MMA, 4 skip split
 };
 
 // elu / tanh are kept out of line: inlining them into the unrolled epilogue makes it tens of KB of straight-line
@@ -86,7 +84,6 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], conv_bar[STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
-    const long long t_begin = clock64();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
     const int nk = (ep.K + TC_BK - 1) / TC_BK;
@@ -119,8 +116,6 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
-    long long *dbg = ep.dbg ? ep.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
-    if (dbg && threadIdx.x == 0) { dbg[0] = t_begin; dbg[1] = clock64(); }
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer
@@ -142,7 +137,6 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             tma_load_2d(st + 2 * A_TILE, &tmW_hi, k0, n0, &full_bar[s]);
             tma_load_2d(st + 2 * A_TILE + W_TILE, &tmW_lo, k0, n0, &full_bar[s]);
         }
-        if (dbg) dbg[2] = clock64();
     } else if (warp == 1 && lane == 0) {
         // ---------------- MMA issuer
         // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
@@ -169,7 +163,6 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             umma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
         }
         umma_commit(&tmem_full_bar);             // accumulator complete
-        if (dbg) dbg[3] = clock64();
     } else if (SPLIT_IN_KERNEL && warp >= 4) {
         // ---------------- converters: raw fp32 tile -> (hi, lo) tf32 pair, elementwise in the swizzled layout
         const int tid = threadIdx.x - 128;        // 0..255: eight converter warps keep the split off the critical path
@@ -217,14 +210,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // with 128-bit stores straight from registers (the L2 merges the sectors of a row).
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (dbg && threadIdx.x == 128) dbg[4] = clock64();
         const int wq = warp & 3;
         const int half = warp >> 2;
         constexpr int HALF_COLS = BN >= 64 ? BN / 2 : BN;      // BN = 32: one 32-column chunk, warps 0..3 only
         const int m = m0 + wq * 32 + lane;
         const bool mok = m < ep.M;
         const bool accumulate = ep.accumulate == 1;
-        const bool no_store = ep.accumulate == 2;      // profiling aid
         const int act = ep.act;
         const float *bias = ep.bias, *row_vec = ep.row_vec, *scale = ep.scale, *shift = ep.shift;
         const float rs = (ep.row_scale && mok) ? __ldg(ep.row_scale + m) : 0.f;
@@ -294,9 +285,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     for (int j = 0; j < 32; ++j)
                         if (whole || nb + j < ep.Nout) v[j] += crow[nb + j];
                 }
-                if (no_store) {
-                    if (v[0] + v[31] == 123.456f) crow[0] = 0.f;
-                } else if (vec && whole) {
+                if (vec && whole) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4 *>(crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -308,10 +297,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
         }
     }
-    if (dbg && threadIdx.x == 128) dbg[5] = clock64();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (dbg && threadIdx.x == 0) dbg[6] = clock64();
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(2 * BN)) : "memory");
@@ -383,7 +370,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
             // The ring holds 3-4 k-steps (48 KB of DRAM reads in flight per SM); under load an HBM round trip is ~3 k
             // cycles, i.e. ~1.5 k cycles per k-step against 768 of MMA work.  The activation rows of this CTA's NEXT
             // tile are therefore pulled into L2 now (no shared memory needed), one whole tile ahead.
-            if (!(ep.mode & 8)) {
+            {
                 const int tn = t + (int)gridDim.x;
                 if (tn < total_tiles) {
                     const int mn = (tn / n_tiles) * TC_BM;
@@ -430,7 +417,6 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
                 for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
                     const uint32_t first = (kt > 0 || k > 0) ? 1u : 0u;
-                    if (ep.mode & 2) continue;
                     umma_tf32(acc_main, a_hi + adv, w_hi + adv, idesc, first);
                     umma_tf32(acc_corr, a_lo + adv, w_hi + adv, idesc, first);
                     umma_tf32(acc_corr, a_hi + adv, w_lo + adv, idesc, 1u);
@@ -454,7 +440,6 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
                 float4 av[NV];
 #pragma unroll
                 for (int i = 0; i < NV; ++i) av[i] = hi[tid + i * 256];
-                if (!(ep.mode & 4))
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     const float4 a = av[i];
@@ -519,7 +504,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tmA1, const __gr
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int nb = n0 + c0;
-                if (nb >= ep.Nout || (ep.mode & 1)) break;            // warp-uniform
+                if (nb >= ep.Nout) break;            // warp-uniform
                 uint32_t r[32], q[32];
                 const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * 2 * BN + c0);
                 asm volatile(
@@ -642,10 +627,6 @@ __global__ void split_a_kernel(const float *__restrict__ A1, int K1, int lda1, c
     *reinterpret_cast<float4 *>(lo + m * K + k) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-void *g_tc_debug = nullptr;
-bool g_tc_force_presplit = false;     // testing aid: exercise the split_a_kernel path
-bool g_tc_no_persistent = false;      // testing aid: keep large problems on the one-tile kernel
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -684,11 +665,8 @@ template <int BN, int STAGES, bool SPLIT>
 static int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &w_hi, const CUtensorMap &w_lo,
                      const TcEpilogue &ep, int K1, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024;
-    static bool attr = false;
-    if (!attr) {
-        GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    // per launch: the attribute belongs to the current device (a process-wide flag would skip a second GPU)
+    GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div(ep.M, TC_BM), (unsigned)ceil_div(ep.Nout, BN));
     tc_linear_kernel<BN, STAGES, SPLIT><<<grid, 384, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, ep, K1);
     GSN_BUMP(1);
@@ -701,11 +679,7 @@ static int launch_tc_persistent(const CUtensorMap &a1, const CUtensorMap &a2, co
                                 const CUtensorMap &c_map, const TcEpilogue &ep, int K1, cudaStream_t stream) {
     // ring | 4 x 4 KB store staging | 3 x BN column constants | alignment slack
     constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 4 * 4096 + 3 * BN * 4 + 1024;
-    static bool attr = false;
-    if (!attr) {
-        GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    GSN_CUDA_OK(cudaFuncSetAttribute(tc_linear_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int m_tiles = (int)ceil_div(ep.M, TC_BM), n_tiles = (int)ceil_div(ep.Nout, BN);
     const int64_t total = (int64_t)m_tiles * n_tiles;
     const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
@@ -754,15 +728,13 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
     int BN = p.Nout > 128 ? 256 : (p.Nout > 64 ? 128 : 64);
     const int64_t m_tiles = ceil_div(p.M, TC_BM);
     if (m_tiles * ceil_div(p.Nout, BN) < kNumSMs / 2 && p.Nout >= 32) BN = 32;
-    static const int tc_mode = getenv("GSN_TC_MODE") ? atoi(getenv("GSN_TC_MODE")) : 0;    // experiment switch, read once
     TcEpilogue ep{p.bias, p.row_scale, p.row_vec, p.tab, p.scale, p.shift, p.tab_idx, p.C,
-                  p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate, (long long *)g_tc_debug,
-                  tc_mode};
+                  p.M, p.Nout, K, p.ldc, p.tab_ld, p.act, p.accumulate};
     CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
     int rc;
     if ((rc = make_map(&mW_hi, d_Whi, p.Nout, K, K, BN))) return rc;
     if ((rc = make_map(&mW_lo, d_Wlo, p.Nout, K, K, BN))) return rc;
-    const bool split_in_kernel = (p.K2 == 0 || p.K1 % TC_BK == 0) && !g_tc_force_presplit;
+    const bool split_in_kernel = (p.K2 == 0 || p.K1 % TC_BK == 0) && p.tc_path != GSN_TC_PATH_PRESPLIT;
     if (split_in_kernel) {
         // raw activations straight through TMA; the tile is split into (hi, lo) in shared memory by the kernel
         if ((rc = make_map(&mA_hi, p.A1, p.M, p.K1, p.lda1, TC_BM))) return rc;
@@ -770,7 +742,7 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
         else mA_lo = mA_hi;
         // large problems: persistent kernel (continuous ring, double-buffered TMEM accumulators)
         const int BNp = p.Nout > 64 ? 128 : 64;
-        if (!g_tc_no_persistent && m_tiles * ceil_div(p.Nout, BNp) >= 2 * kNumSMs && p.ldc % 4 == 0 && al16(p.C)) {
+        if (p.tc_path != GSN_TC_PATH_ONE_TILE && m_tiles * ceil_div(p.Nout, BNp) >= 2 * kNumSMs && p.ldc % 4 == 0 && al16(p.C)) {
             CUtensorMap mC;                       // output tile store: box = 32 rows x 32 columns (128 B), swizzled
             if ((rc = make_map(&mC, p.C, p.M, p.Nout, p.ldc, 32))) return rc;
             if (BNp != BN) {
@@ -799,12 +771,4 @@ extern "C" int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const
     if (BN == 256) return launch_tc<256, 2, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
     if (BN == 128) return launch_tc<128, 3, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
     return launch_tc<64, 4, false>(mA_hi, mA_lo, mW_hi, mW_lo, ep, K, stream);
-}
-
-// profiling aid: when set, every tc_linear CTA writes 8 clock64 stamps to d_buf[cta*8 ..]
-extern "C" int gsn_tc_debug_buffer(void *d_buf) { gsn::g_tc_debug = d_buf; return GSN_OK; }
-extern "C" int gsn_tc_force_presplit(int on) {
-    gsn::g_tc_force_presplit = (on & 1) != 0;
-    gsn::g_tc_no_persistent = (on & 2) != 0;
-    return GSN_OK;
 }

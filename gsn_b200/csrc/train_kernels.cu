@@ -58,50 +58,102 @@ __global__ void __launch_bounds__(256) bag_fwd_kernel(const __grid_constant__ Ba
         for (int i = 0; i < VEC; ++i) dst[i] = acc[i];
 }
 
-// grad_tab_c[v, :] += sum_{r : idx[r, c] = v} grad_out[r, :].  One CTA = (block of rows, column c).  The column's values of
-// the block are staged in shared memory; every warp then owns table rows v = warp, warp + 8, ...: it finds the block's
-// rows holding v with ballots over the staged values and sums their gradient rows in REGISTERS (lanes across d), so the
-// only atomics are one global fp32 add per (table row present in the block, channel) -- no shared-memory atomics, whose
-// fp32 form is a compare-and-swap loop that serialises on the few distinct values of a categorical column.
+// grad_tab_c[v, :] += sum_{r : idx[r, c] = v} grad_out[r, :].  One CTA = (block of 1024 rows, column c); the column's values
+// of the block are staged in shared memory.  No shared-memory fp32 atomics (a compare-and-swap loop that serialises on the
+// few distinct values of a categorical column); the only atomics are one global fp32 add per (table row seen by the
+// block, channel).  Two mappings:
+//   many values (V > 8): every warp OWNS table rows v = warp, warp + 8, ...: it finds the block's rows holding v with
+//                        ballots over the staged values and sums their gradient rows in registers (lanes across d), four
+//                        rows in flight at a time;
+//   few values (V <= 8, e.g. the bond features): every warp takes a slice of the rows and adds each gradient row into its
+//                        private [V, d] buffer in shared memory (plain read-modify-write: one owner per address), four
+//                        rows in flight; the eight buffers are then summed.
 constexpr int kBagRows = 1024;          // rows per CTA
 constexpr int kBagMaxD = 1024;          // channels a lane can hold (32 per lane)
+constexpr int kBagSmallV = 8;
 template <int PER>          // channels per lane: d <= 32 * PER
 __global__ void __launch_bounds__(256) bag_bwd_kernel(const __grid_constant__ BagParams p) {
+    extern __shared__ float bag_buf[];                  // few values: [8 warps][V * d]
     __shared__ int32_t vals[kBagRows];
     const int c = blockIdx.y;
     const int V = p.rows_of[c], d = p.d;
     float *gt = const_cast<float *>(p.tab[c]);
     const int64_t r0 = (int64_t)blockIdx.x * kBagRows;
     const int n = (int)((r0 + kBagRows < p.R ? r0 + kBagRows : p.R) - r0);
+    const bool small = V <= kBagSmallV && p.rows_per_cta != 0;       // rows_per_cta != 0: the launch provided the buffers
     for (int i = threadIdx.x; i < n; i += 256) {
         const int64_t v = __ldg(p.idx + (r0 + i) * p.ld + c);
         vals[i] = (v >= 0 && v < V) ? (int32_t)v : -1;           // out of range: flagged by the forward, skipped here
     }
+    if (small)
+        for (int i = threadIdx.x; i < 8 * V * d; i += 256) bag_buf[i] = 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *gbase = p.grad_out + r0 * d;
+    if (small) {
+        float *mine = bag_buf + (size_t)warp * V * d;
+        const int per_warp = (n + 7) / 8;
+        const int a = warp * per_warp, e = min(n, a + per_warp);
+        for (int r = a; r < e; r += 4) {
+            float g[4][PER];
+            int v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[q] = r + q < e ? vals[r + q] : -1;
+#pragma unroll
+                for (int j = 0; j < PER; ++j)
+                    g[q][j] = (v[q] >= 0 && lane + 32 * j < d) ? __ldg(gbase + (int64_t)(r + q) * d + lane + 32 * j) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (v[q] < 0) continue;
+#pragma unroll
+                for (int j = 0; j < PER; ++j)
+                    if (lane + 32 * j < d) mine[v[q] * d + lane + 32 * j] += g[q][j];
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < V * d; i += 256) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += bag_buf[(size_t)w * V * d + i];
+            if (t != 0.f) atomicAdd(gt + i, t);
+        }
+        return;
+    }
+    __shared__ uint16_t match[8][kBagRows];          // per warp: the block's rows that hold the warp's current value
     for (int v = warp; v < V; v += 8) {
+        int cnt = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool hit = i < n && vals[i] == v;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) match[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+            cnt += __popc(m);
+        }
+        if (cnt == 0) continue;
+        __syncwarp();
         float acc[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) acc[j] = 0.f;
-        bool any = false;
-        for (int base = 0; base < n; base += 32) {
-            const int i = base + lane;
-            unsigned m = __ballot_sync(0xffffffffu, i < n && vals[i] == v);
-            while (m) {
-                const int b = __ffs((int)m) - 1;
-                m &= m - 1;
-                any = true;
-                const float *g = p.grad_out + (r0 + base + b) * d;
+        for (int k = 0; k < cnt; k += 4) {                   // four gradient rows in flight
+            float g[4][PER];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int row = k + q < cnt ? (int)match[warp][k + q] : -1;
 #pragma unroll
                 for (int j = 0; j < PER; ++j)
-                    if (lane + 32 * j < d) acc[j] += __ldg(g + lane + 32 * j);
+                    g[q][j] = (row >= 0 && lane + 32 * j < d) ? __ldg(gbase + (int64_t)row * d + lane + 32 * j) : 0.f;
             }
-        }
-        if (any) {
 #pragma unroll
-            for (int j = 0; j < PER; ++j)
-                if (lane + 32 * j < d) atomicAdd(gt + (int64_t)v * d + lane + 32 * j, acc[j]);
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < PER; ++j) acc[j] += g[q][j];
         }
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+            if (lane + 32 * j < d) atomicAdd(gt + (int64_t)v * d + lane + 32 * j, acc[j]);
+        __syncwarp();
     }
 }
 
@@ -220,9 +272,27 @@ extern "C" int gsn_embedding_bag_bwd(const GsnBagCol *h_grad_cols, int32_t n_col
     if (d > kBagMaxD) return GSN_E_UNSUPPORTED;
     dim3 grid((unsigned)ceil_div(R, kBagRows), (unsigned)n_cols);
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (d <= 128) bag_bwd_kernel<4><<<grid, 256, 0, stream>>>(p);
-    else if (d <= 512) bag_bwd_kernel<16><<<grid, 256, 0, stream>>>(p);
-    else bag_bwd_kernel<32><<<grid, 256, 0, stream>>>(p);
+    // few-valued columns: eight private [V, d] buffers per CTA (<= 8 * 8 * d floats)
+    int vmin = 1 << 30;
+    for (int c = 0; c < n_cols; ++c) vmin = h_grad_cols[c].rows < vmin ? h_grad_cols[c].rows : vmin;
+    size_t smem = 0;
+    if (vmin <= kBagSmallV && (size_t)8 * kBagSmallV * d * sizeof(float) <= 160 * 1024) {
+        smem = (size_t)8 * kBagSmallV * d * sizeof(float);
+        p.rows_per_cta = 1;
+    }
+    if (d <= 128) {
+        GSN_CUDA_OK(cudaFuncSetAttribute(bag_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        bag_bwd_kernel<4><<<grid, 256, smem, stream>>>(p);
+    } else if (d <= 320) {
+        GSN_CUDA_OK(cudaFuncSetAttribute(bag_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        bag_bwd_kernel<10><<<grid, 256, smem, stream>>>(p);
+    } else if (d <= 512) {
+        GSN_CUDA_OK(cudaFuncSetAttribute(bag_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        bag_bwd_kernel<16><<<grid, 256, smem, stream>>>(p);
+    } else {
+        GSN_CUDA_OK(cudaFuncSetAttribute(bag_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        bag_bwd_kernel<32><<<grid, 256, smem, stream>>>(p);
+    }
     GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_embedding_bag_bwd");
     return GSN_OK;

@@ -210,7 +210,7 @@ class GsnLinear(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('A1', 'A2', 'W', 'bias', 'row_scale', 'row_vec', 'tab_idx', 'tab',
                                                'scale', 'shift', 'C')] + \
                [(n, ctypes.c_int32) for n in ('M', 'Nout', 'K1', 'K2', 'lda1', 'lda2', 'ldw', 'ldc', 'tab_ld', 'act',
-                                              'vec_ok', 'accumulate')]
+                                              'vec_ok', 'accumulate', 'tc_path')]
 
 
 class GsnEncodeCol(ctypes.Structure):
@@ -225,7 +225,7 @@ def _dp(t):
 
 # Tensor-core dense tail (tcgen05 3xTF32).  "auto": use it whenever the shapes allow (K % 4 == 0, aligned).
 TENSOR_CORES = 'auto'       # 'auto' | 'off'
-FORCE_PRESPLIT = False       # testing aid (see gsn_tc_force_presplit)
+TC_PATH = 0                  # GsnLinear.tc_path for every call (GSN_TC_PATH_*: 0 auto, 1 pre-split pass, 2 one tile per CTA)
 import weakref
 
 _wsplit_cache = {}          # id(tensor) -> (weakref to the tensor, stamp, hi, lo); evicted when the tensor dies
@@ -283,12 +283,12 @@ def linear(A1, W, bias=None, A2=None, row_scale=None, row_vec=None, tab_idx=None
     p.bias, p.row_scale, p.row_vec = _dp(bias), _dp(row_scale), _dp(row_vec)
     p.tab_idx, p.tab, p.tab_ld = _dp(tab_idx), _dp(tab), (0 if tab is None else tab.stride(0))
     p.scale, p.shift, p.C, p.ldc = _dp(scale), _dp(shift), out.data_ptr(), out.stride(0)
-    p.M, p.Nout, p.act, p.accumulate = M, Nout, ACTIVATIONS[activation], int(accumulate)
+    p.M, p.Nout, p.act, p.accumulate, p.tc_path = M, Nout, ACTIVATIONS[activation], int(accumulate), int(TC_PATH)
     with torch.cuda.device(dev):
         if _tc_eligible(A1, A2, W):
             whi, wlo = split_weight(W)
             ws, nbytes = None, 0
-            if FORCE_PRESPLIT or (p.K2 > 0 and p.K1 % 32 != 0):       # only then the activations need a pre-pass
+            if TC_PATH == 1 or (p.K2 > 0 and p.K1 % 32 != 0):       # only then the activations need a pre-pass
                 nb = ctypes.c_size_t(0)
                 _lib.check(_lib.lib().gsn_tc_linear_workspace_bytes(M, p.K1 + p.K2, ctypes.byref(nb)), 'gsn_tc_linear_workspace_bytes')
                 ws, nbytes = torch.empty(nb.value, dtype=torch.uint8, device=dev), nb.value

@@ -240,7 +240,8 @@ int gsn_mp_general_edge_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const
  *                   + bias[n] ) * scale[n] + shift[n] )                    BatchNorm1d (eval) as scale/shift
  * W: nn.Linear layout [Nout, K1+K2], row stride ldw.  Optional pointers may be NULL
  * (row_scale/row_vec and tab/tab_idx come in pairs).  act: 0 relu, 1 elu, 2 tanh, 3 identity.
- * fp32 FFMA accumulation.  `vec_ok` is filled in by the library.
+ * fp32 FFMA accumulation.  `vec_ok` is filled in by the library.  The library keeps no state between calls (no global
+ * switches, no environment variables): everything that selects a code path is an argument.
  */
 typedef struct GsnLinear {
     const float *A1; const float *A2; const float *W;
@@ -250,7 +251,11 @@ typedef struct GsnLinear {
     float *C;
     int32_t M, Nout, K1, K2, lda1, lda2, ldw, ldc, tab_ld, act, vec_ok;
     int32_t accumulate;      /* 1: C += result (sum of JK projections, models_graph_classification.py:236-240) */
+    int32_t tc_path;         /* gsn_tc_linear_fwd only, GSN_TC_PATH_*: which of its kernels runs (0 = chosen from the shape) */
 } GsnLinear;
+#define GSN_TC_PATH_AUTO 0
+#define GSN_TC_PATH_PRESPLIT 1   /* activations split into (hi, lo) by a pre-pass into d_ws instead of inside the GEMM kernel */
+#define GSN_TC_PATH_ONE_TILE 2   /* one output tile per CTA even where the persistent kernel would be chosen */
 
 int gsn_linear_fwd(const GsnLinear *h_p, void *stream);
 
@@ -268,12 +273,6 @@ int gsn_split_tf32(const float *d_src, int64_t rows, int32_t cols, int32_t ld, f
 int gsn_tc_linear_workspace_bytes(int64_t M, int32_t K, size_t *bytes);
 int gsn_tc_linear_fwd(const GsnLinear *h_p, const float *d_Whi, const float *d_Wlo, void *d_ws, size_t ws_bytes,
                       void *stream);
-/* Profiling aid: non-NULL -> every tc_linear CTA writes 8 clock64 stamps to d_buf[cta*8..]; NULL disables. */
-int gsn_tc_debug_buffer(void *d_buf);
-/* Testing aid (bit mask): 1 forces the pre-split path (split_a_kernel + workspace) even when the in-kernel split
- * applies; 2 keeps large problems on the one-tile kernel instead of the persistent one. */
-int gsn_tc_force_presplit(int on);
-
 /*
  * out[g,:] = sum (mean=1: average) of the rows x[ptr[g] .. ptr[g+1]) : the readouts
  * global_add_pool_sparse / global_mean_pool_sparse (utils_graph_learning.py:23-41) for a

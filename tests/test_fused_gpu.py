@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 MODEL_GOLDEN = torch.load(os.path.join(GOLDEN, 'mp_models.pt'))
 
 
-@pytest.mark.parametrize('mode', ['auto', 'off', 'presplit'])
+@pytest.mark.parametrize('mode', ['auto', 'off', 'presplit', 'one_tile'])
 @pytest.mark.parametrize('M,K1,K2,Nout', [(1, 7, 0, 5), (37, 28, 0, 256), (130, 128, 128, 128), (2924, 156, 0, 128),
                                           (5000, 64, 33, 70), (70000, 128, 128, 128), (128, 128, 0, 1), (300, 8, 0, 24),
                                           (1000, 300, 0, 600), (513, 600, 0, 300), (260, 128, 4, 200),
@@ -24,8 +24,7 @@ def test_linear_kernel_vs_torch(M, K1, K2, Nout, mode, monkeypatch):
     from gsn_b200 import ops
     from gsn_b200 import _lib
     monkeypatch.setattr(ops, 'TENSOR_CORES', 'off' if mode == 'off' else 'auto')
-    monkeypatch.setattr(ops, 'FORCE_PRESPLIT', mode == 'presplit')
-    _lib.lib().gsn_tc_force_presplit(1 if mode == 'presplit' else 0)
+    monkeypatch.setattr(ops, 'TC_PATH', {'presplit': 1, 'one_tile': 2}.get(mode, 0))     # GsnLinear.tc_path, per call
     g = torch.Generator().manual_seed(M + K1)
     A1 = torch.randn((M, K1), generator=g)
     A2 = torch.randn((M, K2), generator=g) if K2 else None
@@ -45,7 +44,6 @@ def test_linear_kernel_vs_torch(M, K1, K2, Nout, mode, monkeypatch):
     acc = out2.clone()
     ops.linear(c(A1), c(W), A2=c(A2), out=acc, accumulate=True)
     torch.testing.assert_close(acc, 2 * out2, atol=1e-5, rtol=1e-5)
-    _lib.lib().gsn_tc_force_presplit(0)
 
 
 def test_pool_ptr_and_encode_rows():
