@@ -700,7 +700,7 @@ def main():
         raise SystemExit('bench.py needs a CUDA device: gsn_b200 has no CPU path (use --impl reference for the CPU arm)')
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep stdout to the single JSON line (no 'NCCL version' banner)
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's banner / debug lines never reach stdout (one JSON line)
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     line = run_ours(args, rank, world, local_rank)
     if rank == 0:

@@ -21,6 +21,8 @@ _ERRORS = {-1: 'GSN_E_INVALID (bad argument)', -2: 'GSN_E_UNSUPPORTED (shape out
            -3: 'GSN_E_WORKSPACE (workspace too small)', -4: 'GSN_E_CUDA'}
 
 S_GRAPH_TOO_LARGE, S_CROSS_GRAPH_EDGE, S_MISSING_EDGE, S_INDEX_RANGE, S_COUNT_OVERFLOW, S_NOT_GROUPED = 1, 2, 4, 8, 16, 32
+S_UNSEEN_VALUE = 64          # informative: an identifier value outside the fitted one_hot_unique vocabulary
+S_FATAL = 63
 
 _vp, _i64, _i32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_size_t
 _szp = ctypes.POINTER(ctypes.c_size_t)
@@ -51,8 +53,8 @@ _SIGNATURES = {
     'gsn_mp_ogb_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     'gsn_fused_model_fwd': (ctypes.c_int, [_vp, _vp]),
     'gsn_pool_ptr': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
-    'gsn_encode_rows': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _vp]),
-    'gsn_encode_rows_grouped': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
+    'gsn_encode_rows': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'gsn_encode_rows_grouped': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     'gsn_dgn_aggregate_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32,
                                              ctypes.c_float, _vp, _vp]),
     'gsn_dgn_aggregate_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32,
@@ -146,4 +148,6 @@ def status_message(bits: int) -> str:
         out.append('a per-vertex / per-edge occurrence count exceeded 2^32 - 1')
     if bits & S_NOT_GROUPED:
         out.append('edge_index columns are not grouped by graph (batch order)')
+    if bits & S_UNSEEN_VALUE:
+        out.append('an identifier value is not in the fitted vocabulary (encoded as the next larger known value)')
     return '; '.join(out)

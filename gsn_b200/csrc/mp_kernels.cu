@@ -614,7 +614,30 @@ struct EncodeParams {
     const int32_t *perm;     // optional: output row r encodes source row perm[r] (rows delivered in CSR order)
     int64_t R;
     int32_t *out;
+    int32_t *status;         // optional
 };
+
+// rank of one categorical value inside its column's table: position among the sorted distinct values (one_hot_unique),
+// or the value itself; values the table cannot hold are clamped and reported instead of indexing past the table
+__device__ __forceinline__ int encode_rank(const GsnEncodeCol &col, const int64_t *vocab, int64_t v, int32_t *status) {
+    if (col.vocab_end > col.vocab_begin) {
+        int lo = col.vocab_begin, hi = col.vocab_end;     // first entry >= v  (torch.bucketize / np.unique inverse)
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(vocab + mid) < v) lo = mid + 1; else hi = mid;
+        }
+        int rank = lo - col.vocab_begin;
+        const int last = col.vocab_end - col.vocab_begin - 1;
+        if (rank > last) rank = last;
+        if (status && __ldg(vocab + col.vocab_begin + rank) != v) atomicOr(status, GSN_S_UNSEEN_VALUE);
+        return rank;
+    }
+    if (col.rows > 0 && (v < 0 || v >= col.rows)) {
+        if (status) atomicOr(status, GSN_S_INDEX_RANGE);
+        return v < 0 ? 0 : col.rows - 1;
+    }
+    return (int)v;
+}
 
 __global__ void encode_rows_kernel(const __grid_constant__ EncodeParams p) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -624,20 +647,7 @@ __global__ void encode_rows_kernel(const __grid_constant__ EncodeParams p) {
     const GsnEncodeCol &col = p.col[c];
     const int64_t rs = p.perm ? (int64_t)__ldg(p.perm + r) : r;
     const int64_t v = __ldg(col.src + rs * col.stride);
-    int rank;
-    if (col.vocab_end > col.vocab_begin) {
-        int lo = col.vocab_begin, hi = col.vocab_end;     // first entry >= v  (torch.bucketize / np.unique inverse)
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(p.vocab + mid) < v) lo = mid + 1; else hi = mid;
-        }
-        rank = lo - col.vocab_begin;
-        const int last = col.vocab_end - col.vocab_begin - 1;
-        if (rank > last) rank = last;
-    } else {
-        rank = (int)v;
-    }
-    p.out[t] = col.table_off + rank;
+    p.out[t] = col.table_off + encode_rank(col, p.vocab, v, p.status);
 }
 
 inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
@@ -793,27 +803,14 @@ __global__ void encode_rows_grouped_kernel(const __grid_constant__ EncodeGrouped
         if (q.group[c] != g) continue;
         const GsnEncodeCol &col = p.col[c];
         const int64_t v = __ldg(col.src + rs * col.stride);
-        int rank;
-        if (col.vocab_end > col.vocab_begin) {
-            int lo = col.vocab_begin, hi = col.vocab_end;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (__ldg(p.vocab + mid) < v) lo = mid + 1; else hi = mid;
-            }
-            rank = lo - col.vocab_begin;
-            const int last = col.vocab_end - col.vocab_begin - 1;
-            if (rank > last) rank = last;
-        } else {
-            rank = (int)v;
-        }
-        acc += col.table_off + rank * q.mult[c];
+        acc += col.table_off + encode_rank(col, p.vocab, v, p.status) * q.mult[c];
     }
     p.out[t] = acc;
 }
 
 extern "C" int gsn_encode_rows_grouped(const GsnEncodeCol *h_cols, int32_t n_cols, const int32_t *h_group,
                                        const int32_t *h_mult, int32_t n_groups, const int64_t *d_vocab,
-                                       const int32_t *d_perm, int64_t R, int32_t *d_out, void *stream_) {
+                                       const int32_t *d_perm, int64_t R, int32_t *d_out, int32_t *d_status, void *stream_) {
     if (!h_cols || !h_group || !h_mult || n_cols < 1 || n_cols > GSN_MAX_ENCODE_COLS || n_groups < 1 || n_groups > n_cols ||
         R < 0 || !d_out)
         return GSN_E_INVALID;
@@ -826,7 +823,7 @@ extern "C" int gsn_encode_rows_grouped(const GsnEncodeCol *h_cols, int32_t n_col
         q.group[i] = h_group[i];
         q.mult[i] = h_mult[i];
     }
-    q.e.n_cols = n_cols; q.e.vocab = d_vocab; q.e.perm = d_perm; q.e.R = R; q.e.out = d_out; q.n_groups = n_groups;
+    q.e.n_cols = n_cols; q.e.vocab = d_vocab; q.e.perm = d_perm; q.e.R = R; q.e.out = d_out; q.e.status = d_status; q.n_groups = n_groups;
     encode_rows_grouped_kernel<<<(unsigned)ceil_div(R * n_groups, 256), 256, 0, (cudaStream_t)stream_>>>(q);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_encode_rows_grouped");
@@ -834,7 +831,7 @@ extern "C" int gsn_encode_rows_grouped(const GsnEncodeCol *h_cols, int32_t n_col
 }
 
 extern "C" int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d_vocab, const int32_t *d_perm,
-                               int64_t R, int32_t *d_out, void *stream_) {
+                               int64_t R, int32_t *d_out, int32_t *d_status, void *stream_) {
     if (!h_cols || n_cols < 1 || n_cols > GSN_MAX_ENCODE_COLS || R < 0 || !d_out) return GSN_E_INVALID;
     if (R == 0) return GSN_OK;
     EncodeParams p;
@@ -843,7 +840,7 @@ extern "C" int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const
         if (h_cols[i].vocab_end > h_cols[i].vocab_begin && !d_vocab) return GSN_E_INVALID;
         p.col[i] = h_cols[i];
     }
-    p.n_cols = n_cols; p.vocab = d_vocab; p.perm = d_perm; p.R = R; p.out = d_out;
+    p.n_cols = n_cols; p.vocab = d_vocab; p.perm = d_perm; p.R = R; p.out = d_out; p.status = d_status;
     encode_rows_kernel<<<(unsigned)ceil_div(R * n_cols, 256), 256, 0, (cudaStream_t)stream_>>>(p);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("gsn_encode_rows");

@@ -100,6 +100,36 @@ def allreduce_gradients(parameters, group=None, average: bool = True):
         off += n
 
 
+class FlatGradients:
+    """The gradients of all trainable parameters as views into ONE fp32 buffer, so that the only collective of the
+    system -- the gradient all-reduce of a training step -- is a single NCCL call on memory that already holds the
+    gradients (no gather into a staging buffer, no copy back): autograd accumulates into an existing .grad in place,
+    so the views survive backward; zero() replaces optimizer.zero_grad().  Works under CUDA-graph capture (static
+    addresses)."""
+
+    def __init__(self, parameters):
+        self.params = [p for p in parameters if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else 'cpu'
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise TypeError('FlatGradients: fp32 parameters only')
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self, group=None, average: bool = True):
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            self.flat.mul_(1.0 / dist.get_world_size(group))
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
     """replicate the weights of rank `src` (start of training)"""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

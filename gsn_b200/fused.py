@@ -145,6 +145,7 @@ class FusedForward:
                 if ef_cat:
                     edge_tables.append(Wq_ef.t().contiguous())
                     L['Wq_ef'] = None
+                    L['ef_rows'] = int(Wq_ef.shape[1])
                 else:
                     L['Wq_ef'] = Wq_ef.contiguous()
             L['Te'] = torch.cat(edge_tables, 0).contiguous() if edge_tables else None
@@ -238,27 +239,33 @@ class FusedForward:
         efi = None
         if getattr(data, 'edge_features', None) is not None:
             efi = data.edge_features if data.edge_features.dim() == 2 else data.edge_features.unsqueeze(-1)
-        return {'ids': ids, 'id_off': id_off, 'vcat': vcat, 'vptr': vptr, 'xi': xi, 'x': x, 'efi': efi,
+        dev0 = data.edge_index.device
+        if getattr(self, 'status', None) is None or self.status.device != dev0:
+            self.status = torch.zeros(1, dtype=torch.int32, device=dev0)
+        return {'ids': ids, 'id_off': id_off, 'vcat': vcat, 'vptr': vptr, 'xi': xi, 'x': x, 'efi': efi, 'status': self.status,
                 'N': data.x.shape[0], 'E': data.edge_index.shape[1], 'dev': data.edge_index.device, 'ef_rows_cache': {}}
 
     def _layer_rows(self, L, ctx, plan):
         """(node_rows int32 [N, n_node_cols] | None, edge_rows int32 [E, n_groups] in CSR order | None) of one layer"""
         ids, vptr, id_off, vcat, dev = ctx['ids'], ctx['vptr'], ctx['id_off'], ctx['vcat'], ctx['dev']
         node_cols, edge_cols = [], []
+        m = self.model
         if L['x_cat']:
-            node_cols.append((ctx['xi'][:, 0], None, 0))
+            node_cols.append((ctx['xi'][:, 0], None, 0, int(m.input_node_encoder.encoder.d_in[0])))
         if L['uses_ids']:
-            cols = [(ids[:, c], vptr[c], id_off[c]) for c in range(ids.shape[1])]
+            id_dims = m.id_encoder[0].encoder.d_in
+            cols = [(ids[:, c], vptr[c], id_off[c], 0 if vptr[c] is not None else int(id_dims[c])) for c in range(ids.shape[1])]
             if L['local']:
                 edge_cols += cols
             else:
-                node_cols += [(s, v, off + L['Tn_off_ids']) for s, v, off in cols]
+                node_cols += [(s, v, off + L['Tn_off_ids'], r) for s, v, off, r in cols]
         if L['uses_ef'] and L['ef_cat']:
-            edge_cols.append((ctx['efi'][:, 0], None, L['Te_off_ef']))
+            edge_cols.append((ctx['efi'][:, 0], None, L['Te_off_ef'], int(L['ef_rows'])))
         eg = L['edge_groups']
         if eg is not None:
-            edge_cols = [(s, v, eg['off'][c]) for c, (s, v, _) in enumerate(edge_cols)]
-        node_rows = ops.encode_rows(node_cols, vcat, ctx['N'], dev) if node_cols else None
+            edge_cols = [(s, v, eg['off'][c], r) for c, (s, v, _, r) in enumerate(edge_cols)]
+        st = ctx['status']
+        node_rows = ops.encode_rows(node_cols, vcat, ctx['N'], dev, status=st) if node_cols else None
         # edge rows are produced directly in CSR order (perm = plan.eid): the message kernel then reads them
         # sequentially instead of chasing eid -> row
         only_ef = len(edge_cols) == 1 and L['uses_ef'] and L['ef_cat']
@@ -268,9 +275,9 @@ class FusedForward:
             return node_rows, cache[key]
         if eg is not None:
             edge_rows = ops.encode_rows_grouped(edge_cols, eg['group'], eg['mult'], eg['n_groups'], vcat, ctx['E'], dev,
-                                                perm=plan.eid)
+                                                perm=plan.eid, status=st)
         else:
-            edge_rows = ops.encode_rows(edge_cols, vcat, ctx['E'], dev, perm=plan.eid) if edge_cols else None
+            edge_rows = ops.encode_rows(edge_cols, vcat, ctx['E'], dev, perm=plan.eid, status=st) if edge_cols else None
         if only_ef:
             cache[key] = edge_rows
         return node_rows, edge_rows

@@ -94,7 +94,6 @@ class FusedModel(FusedForward):
             raise NotImplementedError('fused model kernel: unsupported model configuration')
         self.graphs_per_unit = graphs_per_unit
         self._fm_stamp = None
-        self.status: Optional[torch.Tensor] = None
         self.debug_x_out = False
         self.last_x_out: List[torch.Tensor] = []
 
@@ -187,8 +186,6 @@ class FusedModel(FusedForward):
         if len(flows) != 1:
             raise NotImplementedError('fused model kernel: layers with different flow directions')
         plan = ops.edge_plan(data.edge_index, N, flows.pop())
-        if self.status is None or self.status.device != dev:
-            self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         mean = m.readout == 'mean'
         fm = GsnFusedModel()
         keep = []
@@ -243,6 +240,6 @@ class FusedModel(FusedForward):
         return self._project(pooled_list)
 
     def raise_on_status(self):
-        bits = int(self.status.item()) if self.status is not None else 0
+        bits = (int(self.status.item()) if getattr(self, 'status', None) is not None else 0) & _lib.S_FATAL
         if bits:
             raise RuntimeError('fused model kernel: ' + _lib.status_message(bits))

@@ -41,7 +41,8 @@ class EdgePlan:
     messages are summed at edge_index[1] and x_j is gathered at edge_index[0]
     (GSN_sparse.py:125-129)."""
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int, flow: str = 'source_to_target'):
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, flow: str = 'source_to_target',
+                 status: Optional[torch.Tensor] = None):
         _lib.require_cuda(edge_index, 'edge_index')
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise ValueError('edge_index must be int64 [2, E]')
@@ -55,7 +56,9 @@ class EdgePlan:
         self.rowptr = torch.empty(self.N + 1, dtype=torch.int32, device=dev)
         self.eid = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
         self.nbr = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
-        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        # device-side status word (GSN_S_INDEX_RANGE for ids outside [0, N)): the caller's, so that one check at the
+        # end of a step covers the plan too, or a private one read by raise_on_status()
+        self.status = status if status is not None else torch.zeros(1, dtype=torch.int32, device=dev)
         L = _lib.lib()
         nb = ctypes.c_size_t(0)
         _lib.check(L.gsn_csr_workspace_bytes(self.N, self.E, ctypes.byref(nb)), 'gsn_csr_workspace_bytes')
@@ -83,15 +86,21 @@ _plan_cache: List[Tuple[tuple, EdgePlan]] = []
 _PLAN_CACHE_SIZE = 8
 
 
-def edge_plan(edge_index: torch.Tensor, num_nodes: int, flow: str = 'source_to_target') -> EdgePlan:
+CHECK_PLANS = False      # True (tests): synchronise and raise IndexError on a malformed edge_index when a plan is built
+
+
+def edge_plan(edge_index: torch.Tensor, num_nodes: int, flow: str = 'source_to_target',
+              status: Optional[torch.Tensor] = None) -> EdgePlan:
     """Cached EdgePlan: the layers of one model see the same edge_index tensor, so
-    the CSR is built once per batch, not once per layer."""
+    the CSR is built once per batch, not once per layer.  status: see EdgePlan."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), flow,
            edge_index.device.index)
     for k, p in _plan_cache:
         if k == key and p.edge_index.data_ptr() == edge_index.data_ptr():
             return p
-    p = EdgePlan(edge_index, num_nodes, flow)
+    p = EdgePlan(edge_index, num_nodes, flow, status)
+    if CHECK_PLANS:
+        p.raise_on_status()
     _plan_cache.append((key, p))
     if len(_plan_cache) > _PLAN_CACHE_SIZE:
         _plan_cache.pop(0)
@@ -216,7 +225,7 @@ class GsnLinear(ctypes.Structure):
 class GsnEncodeCol(ctypes.Structure):
     """ctypes image of `struct GsnEncodeCol`."""
     _fields_ = [('src', ctypes.c_void_p), ('stride', ctypes.c_int64), ('vocab_begin', ctypes.c_int32),
-                ('vocab_end', ctypes.c_int32), ('table_off', ctypes.c_int32), ('_pad', ctypes.c_int32)]
+                ('vocab_end', ctypes.c_int32), ('table_off', ctypes.c_int32), ('rows', ctypes.c_int32)]
 
 
 def _dp(t):
@@ -310,41 +319,44 @@ def pool_ptr(x, node_ptr, mean=False):
     return out
 
 
-def encode_rows(columns, vocab, num_rows, device, perm=None):
-    """columns: list of (int64 tensor view [R] (any stride), (vocab_begin, vocab_end) or None, table_off).
-    Returns int32 [R, len(columns)] rows into a concatenated embedding table; with perm (int32 [R], e.g.
-    EdgePlan.eid) output row r encodes source row perm[r]."""
+def _encode_cols(columns):
+    """columns: (int64 view [R], (vocab_begin, vocab_end) | None, table_off[, rows]); rows = number of categories of an
+    identity column (0 / absent: unchecked)"""
     cols = (GsnEncodeCol * len(columns))()
-    for i, (src, vr, off) in enumerate(columns):
+    for i, col in enumerate(columns):
+        src, vr, off = col[0], col[1], col[2]
         if src.dtype != torch.int64:
             raise ValueError('categorical columns must be int64')
         cols[i].src, cols[i].stride = src.data_ptr(), (src.stride(0) if src.dim() else 1)
         cols[i].vocab_begin, cols[i].vocab_end = (0, 0) if vr is None else (int(vr[0]), int(vr[1]))
         cols[i].table_off = int(off)
+        cols[i].rows = int(col[3]) if len(col) > 3 and col[3] else 0
+    return cols
+
+
+def encode_rows(columns, vocab, num_rows, device, perm=None, status=None):
+    """columns: list of (int64 tensor view [R] (any stride), (vocab_begin, vocab_end) or None, table_off[, rows]).
+    Returns int32 [R, len(columns)] rows into a concatenated embedding table; with perm (int32 [R], e.g.
+    EdgePlan.eid) output row r encodes source row perm[r].  status (int32 [1], optional): out-of-range / unseen values."""
+    cols = _encode_cols(columns)
     out = torch.empty((num_rows, len(columns)), dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         _lib.call('encode_rows', 'gsn_encode_rows', ctypes.cast(cols, ctypes.c_void_p), len(columns), _lib.ptr(vocab),
-                  _lib.ptr(perm), num_rows, _lib.ptr(out), _lib.stream_ptr())
+                  _lib.ptr(perm), num_rows, _lib.ptr(out), _lib.ptr(status), _lib.stream_ptr())
     return out
 
 
-def encode_rows_grouped(columns, groups, mults, n_groups, vocab, num_rows, device, perm=None):
+def encode_rows_grouped(columns, groups, mults, n_groups, vocab, num_rows, device, perm=None, status=None):
     """encode_rows with the columns of a group folded into one mixed-radix row index (gsn_encode_rows_grouped):
     out[r, g] = sum_{c in group g} (table_off_c + rank_c * mult_c)"""
-    cols = (GsnEncodeCol * len(columns))()
-    for i, (src, vr, off) in enumerate(columns):
-        if src.dtype != torch.int64:
-            raise ValueError('categorical columns must be int64')
-        cols[i].src, cols[i].stride = src.data_ptr(), (src.stride(0) if src.dim() else 1)
-        cols[i].vocab_begin, cols[i].vocab_end = (0, 0) if vr is None else (int(vr[0]), int(vr[1]))
-        cols[i].table_off = int(off)
+    cols = _encode_cols(columns)
     gr = (ctypes.c_int32 * len(columns))(*[int(g) for g in groups])
     mu = (ctypes.c_int32 * len(columns))(*[int(m) for m in mults])
     out = torch.empty((num_rows, n_groups), dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         _lib.call('encode_rows', 'gsn_encode_rows_grouped', ctypes.cast(cols, ctypes.c_void_p), len(columns),
                   ctypes.cast(gr, ctypes.c_void_p), ctypes.cast(mu, ctypes.c_void_p), n_groups, _lib.ptr(vocab),
-                  _lib.ptr(perm), num_rows, _lib.ptr(out), _lib.stream_ptr())
+                  _lib.ptr(perm), num_rows, _lib.ptr(out), _lib.ptr(status), _lib.stream_ptr())
     return out
 
 

@@ -53,6 +53,8 @@ extern "C" {
 #define GSN_S_INDEX_RANGE 8     /* a node id outside [0,N) */
 #define GSN_S_COUNT_OVERFLOW 16 /* a per-vertex / per-edge count exceeded 2^32 - 1 inside a CTA-private accumulator */
 #define GSN_S_NOT_GROUPED 32    /* gsn_count_small: edge_index columns are not grouped by graph (PyG collate order) */
+#define GSN_S_UNSEEN_VALUE 64   /* gsn_encode_rows: a value that is not in the one_hot_unique vocabulary (encoded as the next
+                                   larger known value; informative, the reference cannot encode such a value at all) */
 
 #define GSN_MAXK 16             /* max pattern vertices */
 
@@ -293,12 +295,15 @@ typedef struct GsnEncodeCol {
     const int64_t *src;      /* device */
     int64_t stride;          /* elements between consecutive rows */
     int32_t vocab_begin, vocab_end;   /* into d_vocab; begin == end: identity */
-    int32_t table_off, _pad;
+    int32_t table_off;
+    int32_t rows;            /* identity columns: number of categories (0 = unchecked); a value outside [0, rows) sets
+                                GSN_S_INDEX_RANGE and is clamped (the reference's one-hot scatter_ / nn.Embedding raises) */
 } GsnEncodeCol;
 
 #define GSN_MAX_ENCODE_COLS 16
 int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d_vocab, const int32_t *d_perm, int64_t R,
-                    int32_t *d_out, void *stream);   /* d_perm (optional): out row r encodes source row d_perm[r] */
+                    int32_t *d_out, int32_t *d_status, void *stream);
+/* d_perm (optional): out row r encodes source row d_perm[r];  d_status (optional): GSN_S_INDEX_RANGE / GSN_S_UNSEEN_VALUE */
 
 /* Grouped form: columns with the same h_group[c] are folded into ONE output column as a mixed-radix number,
  *   out[r, g] = sum_{c in g} (table_off_c + rank_c * h_mult[c]),
@@ -306,7 +311,7 @@ int gsn_encode_rows(const GsnEncodeCol *h_cols, int32_t n_cols, const int64_t *d
  * kernel then gathers one table row per group instead of one per column. */
 int gsn_encode_rows_grouped(const GsnEncodeCol *h_cols, int32_t n_cols, const int32_t *h_group, const int32_t *h_mult,
                             int32_t n_groups, const int64_t *d_vocab, const int32_t *d_perm, int64_t R, int32_t *d_out,
-                            void *stream);
+                            int32_t *d_status, void *stream);
 
 /*
  * 'general' message kind with categorical inputs kept as indices (layer 0 of the ZINC /

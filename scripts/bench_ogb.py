@@ -82,7 +82,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', 0))
     gpu_impl = a.impl in ('ours', 'eager_torch')
     if world > 1 and gpu_impl:
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')       # stdout carries the JSON line only
         torch.cuda.set_device(local)
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
     from gsn_b200.synthetic import zinc_like_batch
@@ -144,9 +144,14 @@ def main():
             gd.broadcast_parameters(model, src=0)
         params = [p_ for p_ in model.parameters()]
         from gsn_b200 import _lib
+        from gsn_b200.distributed import FlatGradients
+        fg = FlatGradients(params) if a.impl == 'ours' else None      # gradients live in one flat buffer: 1 NCCL call
 
         def fwd_bwd():
-            opt.zero_grad(set_to_none=True)
+            if fg is not None:
+                fg.zero()
+            else:
+                opt.zero_grad(set_to_none=True)
             loss = torch.nn.functional.binary_cross_entropy_with_logits(model(data), yd)
             loss.backward()
             return loss
@@ -154,7 +159,7 @@ def main():
         def step():
             loss = fwd_bwd()
             if world > 1:
-                gd.allreduce_gradients(params)          # one flat fp32 buffer, averaged
+                fg.allreduce() if fg is not None else gd.allreduce_gradients(params)     # one flat fp32 buffer, averaged
             opt.step()
             return loss
         ar_ms = None
@@ -170,7 +175,6 @@ def main():
             torch.cuda.synchronize()
             l0 = _lib.launch_count()
             g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(g_fb):
                 static_loss = fwd_bwd()
             own_launches = _lib.launch_count() - l0
@@ -180,7 +184,7 @@ def main():
             def step():                                  # noqa: F811
                 g_fb.replay()
                 if world > 1:
-                    gd.allreduce_gradients(params)
+                    fg.allreduce()
                 g_opt.replay()
                 return static_loss
             for _ in range(a.warmup):
@@ -190,7 +194,7 @@ def main():
                 e0, e1 = ev(), ev()
                 e0.record()
                 for _ in range(a.steps):
-                    gd.allreduce_gradients(params)
+                    fg.allreduce()
                 e1.record()
                 torch.cuda.synchronize()
                 ar_ms = e0.elapsed_time(e1) / a.steps

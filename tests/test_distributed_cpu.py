@@ -136,3 +136,43 @@ def test_two_rank_gloo_sharded_dataset_cache(tmp_path):
         assert p.exitcode == 0
     for rank, *oks in res:
         assert all(oks), (rank, oks)
+
+
+def _flat_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from gsn_b200.distributed import FlatGradients
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 3)
+    unused = torch.nn.Parameter(torch.ones(2))               # never receives a gradient: stays zero, layout identical
+    fg = FlatGradients(list(lin.parameters()) + [unused])
+    for step in range(2):
+        fg.zero()
+        x = torch.full((5, 4), float(rank + 1 + step))
+        lin(x).sum().backward()                              # accumulates into the views, in place
+        assert lin.weight.grad.data_ptr() == fg.flat.data_ptr()
+        fg.allreduce()
+        q.put((rank, step, lin.weight.grad.clone(), unused.grad.clone()))
+    dist.destroy_process_group()
+
+
+def test_flat_gradients_allreduce_world2():
+    """FlatGradients: .grad views into one buffer survive backward, one all-reduce averages them over the ranks"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    ps = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(4)]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step in range(2):
+        ws = [g for g in got if g[1] == step]
+        exp = torch.full((3, 4), 5.0 * ((1 + step) + (2 + step)) / 2)          # d/dW sum(W x) = sum over 5 rows of x
+        for _, _, w, u in ws:
+            torch.testing.assert_close(w, exp)
+            assert float(u.abs().max()) == 0.0
