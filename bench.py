@@ -216,7 +216,7 @@ def run_ours(args, rank, world, local_rank):
         got_v = bps[-1].run(keys[v], pool_dev[v], G).clone()
         torch.cuda.synchronize()
         assert torch.allclose(got_v, exp_v, atol=1e-5, rtol=1e-5), 'padded + captured step differs from the eager step'
-        assert int(pipe.last_status.item()) == 0 and int(pipe.fused.status.item()) == 0
+        assert int(pipe.last_status.item()) & _lib.S_FATAL == 0 and int(pipe.fused.status.item()) & _lib.S_FATAL == 0
     dev_in = to_tensors(raw[0], device=dev)
     with torch.no_grad():
         ref_out = pipe.step(dev_in).clone()
@@ -692,9 +692,18 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    # the driver reads ONE JSON line from stdout: everything else this process (or a library: NCCL prints its version
+    # banner to stdout) writes goes to stderr; the line itself is written to the saved descriptor at the end
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    sys.stdout.flush()
+    os.dup2(2, 1)
+
+    def emit(line):
+        real_stdout.write(json.dumps(line) + '\n')
+        real_stdout.flush()
     if args.impl == 'reference':
         if rank == 0:
-            print(json.dumps(run_reference(args)), flush=True)
+            emit(run_reference(args))
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: gsn_b200 has no CPU path (use --impl reference for the CPU arm)')
@@ -704,7 +713,7 @@ def main():
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     line = run_ours(args, rank, world, local_rank)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -35,6 +35,7 @@ struct CountParams {
     int32_t smem_row_words;  // capacity of the rowptr stage (int32)
     int32_t smem_acc_words;  // capacity of the accumulator stage (uint32)
     int32_t parts;           // sub-items per directed edge (small batches: shorter critical path)
+    int32_t warp_items;      // 1: one WARP per directed edge, the 32 lanes split its third-level candidates (dense graphs)
     int64_t *out;            // vertex scope: [N, out_ld] ; edge scope: unused here
     int64_t out_ld;
     uint32_t *slot_acc;      // edge scope: [S, n_cols]
@@ -166,10 +167,21 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
     const uint64_t *adj_base = stage ? sm_adj + (v0 * W - aw0) : prm.adj + v0 * W;       // row of node v0
     const int32_t *row_base = stage ? sm_row + (v0 - rw0) : prm.rowptr + v0;             // rowptr of node v0
 
-    const int parts = prm.parts;
+    const int parts = prm.warp_items ? 32 : prm.parts;
     while (true) {
-        int it = atomicAdd(&ticket, 1);
-        if (it >= ns * parts) break;
+        // dense graphs: a directed edge can root thousands of occurrences (IMDB-BINARY: 5,576 K5 on one edge), so the
+        // item goes to a whole warp and the lanes take every 32nd third-level candidate; sparse graphs: one thread each
+        int it;
+        if (prm.warp_items) {
+            it = (threadIdx.x & 31) == 0 ? atomicAdd(&ticket, 32) : 0;
+            it = __shfl_sync(0xffffffffu, it, 0) + (threadIdx.x & 31);
+        } else {
+            it = atomicAdd(&ticket, 1);
+        }
+        if (it >= ns * parts) {
+            if (prm.warp_items) break;       // warp-uniform: it / 32 is the same for all lanes
+            break;
+        }
         const int s = s0 + it / parts;
         const int part = it % parts;
         const int a = prm.slot_src[s], b = prm.slot_dst[s];
@@ -311,6 +323,8 @@ extern "C" int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t
     prm.T = (int32_t)T;
     // few items (small batch): split every directed edge into sub-items so that more threads share the search
     prm.parts = E < (int64_t)kNumSMs * 128 ? 8 : (E < (int64_t)kNumSMs * 512 ? 4 : (E < (int64_t)kNumSMs * 2048 ? 2 : 1));
+    // average degree >= 8: heavy, skewed items -> warp per item
+    prm.warp_items = avg_deg >= 8.0 ? 1 : 0;
     prm.smem_adj_words = (int32_t)adj_words;
     prm.smem_row_words = (int32_t)row_words;
     prm.smem_acc_words = (int32_t)acc_words;

@@ -49,6 +49,13 @@ def shard_batch(batch: Dict[str, np.ndarray], world: int, rank: int, balance: st
         w = np.diff(edge_ptr)
     elif balance == 'nodes':
         w = np.diff(node_ptr)
+    elif balance.startswith('deg_pow'):
+        # COUNT of k-vertex patterns: the work of a vertex grows like deg^(k-1) ("balanced by sum deg^2
+        # or edge count"); 'deg_pow3' = sum over the graph's vertices of deg^3, ...
+        power = float(balance[len('deg_pow'):] or 2)
+        deg = np.bincount(batch['edge_index'][0], minlength=int(node_ptr[-1])).astype(np.float64)
+        w = np.add.reduceat(deg ** power, node_ptr[:-1].clip(max=max(int(node_ptr[-1]) - 1, 0))) if G else np.zeros(0)
+        w = np.where(np.diff(node_ptr) > 0, w, 0.0)
     else:
         raise ValueError(balance)
     g0, g1 = shard_ranges(w, world)[rank]

@@ -83,14 +83,15 @@ class GSNPipeline:
         N, G = int(t['x'].shape[0]), int(t['node_ptr'].numel() - 1)
         # the grouping of edge_index for the message kernels does not depend on COUNT: build it on a side stream
         # while the counting kernels run (a fork / join that CUDA-graph capture records as parallel branches)
+        # one device-side status word per step: COUNT, the CSR build and the encoders OR their GSN_S_* bits into it
+        status = torch.zeros(1, dtype=torch.int32, device=t['edge_index'].device)
         cur = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             flow = self.model.conv[0].flow
-            ops.edge_plan(t['edge_index'], N, flow).degree()
-        status = torch.zeros(1, dtype=torch.int32, device=t['edge_index'].device)
+            ops.edge_plan(t['edge_index'], N, flow, status=status).degree()
         ids = counting.count_batch(t['edge_index'], t['node_ptr'], self.subgraph_dicts, self.induced, self.id_scope,
                                    num_nodes=N, max_nodes_per_graph=self.max_nodes, check=False, status=status)
         self.last_status = status

@@ -35,7 +35,7 @@ def main():
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         torch.distributed.init_process_group('nccl', device_id=dev)
     import networkx as nx
     from gsn_b200 import counting, distributed as gd, patterns
@@ -49,7 +49,7 @@ def main():
     gold = z['identifiers'].astype(np.int64)
     full = {'edge_index': ei, 'node_ptr': node_ptr, 'edge_ptr': edge_ptr,
             'batch': np.repeat(np.arange(1000), np.diff(node_ptr)), 'gold': gold, 'num_graphs': 1000}
-    shard = gd.shard_batch(full, world, rank, balance='edges')
+    shard = gd.shard_batch(full, world, rank, balance='deg_pow4')       # K5: work per vertex ~ deg^4
     sds = patterns.make_subgraph_dicts([list(nx.complete_graph(k).edges) for k in (3, 4, 5)], 'local')
     ei_t, ptr_t = torch.from_numpy(shard['edge_index']).to(dev), torch.from_numpy(shard['node_ptr'])
     max_n = int(np.diff(node_ptr).max())

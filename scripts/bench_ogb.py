@@ -78,6 +78,9 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='eager training step (no CUDA graph)')
     ap.add_argument('--profile', action='store_true', help='torch.profiler table of the eager step (top kernels by device time)')
     a = ap.parse_args()
+    real_stdout = os.fdopen(os.dup(1), 'w')      # stdout carries the JSON line only (NCCL prints a banner to stdout)
+    sys.stdout.flush()
+    os.dup2(2, 1)
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     gpu_impl = a.impl in ('ours', 'eager_torch')
@@ -271,7 +274,8 @@ def main():
                    note='unmodified reference model (models_graph_classification_ogb_original.py) on the host CPU, PyTorch '
                         'threads = cores; identifiers random (graph-tool absent, COUNT not timed)')
     if rank == 0:
-        print(json.dumps(res))
+        real_stdout.write(json.dumps(res) + '\n')
+        real_stdout.flush()
     if world > 1 and gpu_impl:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
