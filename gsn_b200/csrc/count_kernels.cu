@@ -35,7 +35,7 @@ struct CountParams {
     int32_t smem_row_words;  // capacity of the rowptr stage (int32)
     int32_t smem_acc_words;  // capacity of the accumulator stage (uint32)
     int32_t parts;           // sub-items per directed edge (small batches: shorter critical path)
-    int32_t warp_items;      // 1: one WARP per directed edge, the 32 lanes split its third-level candidates (dense graphs)
+    int32_t warp_items;      // 1: heavy directed edges go to a whole WARP, the 32 lanes split their third-level candidates
     int64_t *out;            // vertex scope: [N, out_ld] ; edge scope: unused here
     int64_t out_ld;
     uint32_t *slot_acc;      // edge scope: [S, n_cols]
@@ -97,12 +97,15 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t n, 
 }
 
 constexpr int kCountThreads = 128;
+constexpr int kHeavyItem = 24;      // third-level candidates from which an item is processed by a whole warp
+constexpr int kHeavyCap = 1024;     // deferred heavy items per chunk
 
 template <int W>
 __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_constant__ CountParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    __shared__ int ticket;
+    __shared__ int ticket, heavy_n, heavy_ticket;
+    __shared__ int heavy[kHeavyCap];
     __shared__ int64_t sh_range[2];
 
     const GsnPlan &P = prm.plan;
@@ -120,6 +123,8 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
         sh_range[0] = prm.node_ptr[g_lo];
         sh_range[1] = prm.node_ptr[g_hi];
         ticket = 0;
+        heavy_n = 0;
+        heavy_ticket = 0;
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
@@ -167,33 +172,56 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
     const uint64_t *adj_base = stage ? sm_adj + (v0 * W - aw0) : prm.adj + v0 * W;       // row of node v0
     const int32_t *row_base = stage ? sm_row + (v0 - rw0) : prm.rowptr + v0;             // rowptr of node v0
 
-    const int parts = prm.warp_items ? 32 : prm.parts;
-    while (true) {
-        // dense graphs: a directed edge can root thousands of occurrences (IMDB-BINARY: 5,576 K5 on one edge), so the
-        // item goes to a whole warp and the lanes take every 32nd third-level candidate; sparse graphs: one thread each
-        int it;
-        if (prm.warp_items) {
-            it = (threadIdx.x & 31) == 0 ? atomicAdd(&ticket, 32) : 0;
-            it = __shfl_sync(0xffffffffu, it, 0) + (threadIdx.x & 31);
-        } else {
-            it = atomicAdd(&ticket, 1);
-        }
-        if (it >= ns * parts) {
-            if (prm.warp_items) break;       // warp-uniform: it / 32 is the same for all lanes
-            break;
-        }
-        const int s = s0 + it / parts;
-        const int part = it % parts;
+    auto process = [&](int s, int part, int nparts) {
         const int a = prm.slot_src[s], b = prm.slot_dst[s];
         const int gb = prm.nbase[a];                      // first node of the graph
         const int off = (int)(gb - v0);
         GraphView<W> G{adj_base + (size_t)off * W, row_base + off};
         if (acc_in_smem) {
             SmemAcc acc{sm_acc, C, off, s0, prm.status};
-            run_item<W>(P, G, a - gb, b - gb, acc, part, parts);
+            run_item<W>(P, G, a - gb, b - gb, acc, part, nparts);
         } else {
             GlobalAcc acc{(unsigned long long *)(prm.out + P.col0), prm.out_ld, (int64_t)gb, prm.slot_acc, C, prm.status};
-            run_item<W>(P, G, a - gb, b - gb, acc, part, parts);
+            run_item<W>(P, G, a - gb, b - gb, acc, part, nparts);
+        }
+    };
+    // how many third-level candidates an item has (cliques: common neighbours; otherwise the degree of b): an item
+    // above the threshold is HEAVY -- a directed edge of a dense graph can root thousands of occurrences (IMDB-BINARY:
+    // 5,576 K5 on one edge) and would be a serial tail on one thread
+    auto weight = [&](int s) -> int {
+        const int a = prm.slot_src[s], b = prm.slot_dst[s];
+        const int gb = prm.nbase[a];
+        const uint64_t *ra = adj_base + (size_t)(a - v0) * W, *rb = adj_base + (size_t)(b - v0) * W;
+        int c = 0;
+        for (int i = 0; i < W; ++i) c += __popcll(P.family == GSN_FAMILY_CLIQUES ? (ra[i] & rb[i]) : rb[i]);
+        (void)gb;
+        return c;
+    };
+    const int parts = prm.parts;
+    while (true) {
+        const int it = atomicAdd(&ticket, 1);
+        if (it >= ns * parts) break;
+        const int s = s0 + it / parts;
+        if (prm.warp_items && weight(s) >= kHeavyItem) {
+            // deferred: after the light items, whole warps take the heavy ones and their lanes split the third level
+            if (it % parts == 0) {
+                const int at = atomicAdd(&heavy_n, 1);
+                if (at < kHeavyCap) heavy[at] = s;
+                else for (int q = 0; q < parts; ++q) process(s, q, parts);       // list full: run it here
+            }
+            continue;
+        }
+        process(s, it % parts, parts);
+    }
+    if (prm.warp_items) {
+        __syncthreads();
+        const int nh = heavy_n < kHeavyCap ? heavy_n : kHeavyCap;
+        const int lane = threadIdx.x & 31;
+        while (true) {
+            int k = lane == 0 ? atomicAdd(&heavy_ticket, 1) : 0;
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= nh) break;
+            process(heavy[k], lane, 32);
         }
     }
     if (!acc_in_smem) return;
@@ -323,7 +351,7 @@ extern "C" int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t
     prm.T = (int32_t)T;
     // few items (small batch): split every directed edge into sub-items so that more threads share the search
     prm.parts = E < (int64_t)kNumSMs * 128 ? 8 : (E < (int64_t)kNumSMs * 512 ? 4 : (E < (int64_t)kNumSMs * 2048 ? 2 : 1));
-    // average degree >= 8: heavy, skewed items -> warp per item
+    // average degree >= 8: skewed item weights -> heavy items are deferred to whole warps
     prm.warp_items = avg_deg >= 8.0 ? 1 : 0;
     prm.smem_adj_words = (int32_t)adj_words;
     prm.smem_row_words = (int32_t)row_words;
