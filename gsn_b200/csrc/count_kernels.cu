@@ -35,7 +35,8 @@ struct CountParams {
     int32_t smem_row_words;  // capacity of the rowptr stage (int32)
     int32_t smem_acc_words;  // capacity of the accumulator stage (uint32)
     int32_t parts;           // sub-items per directed edge (small batches: shorter critical path)
-    int32_t warp_items;      // 1: heavy directed edges go to a whole WARP, the 32 lanes split their third-level candidates
+    int32_t warp_items;      // 1: heavy directed edges are deferred to count_heavy_kernel (whole warps, all SMs)
+    int32_t *heavy;          // global: [0] number of deferred items, [1] work ticket, [4..] their slots
     int64_t *out;            // vertex scope: [N, out_ld] ; edge scope: unused here
     int64_t out_ld;
     uint32_t *slot_acc;      // edge scope: [S, n_cols]
@@ -98,14 +99,13 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t n, 
 
 constexpr int kCountThreads = 128;
 constexpr int kHeavyItem = 24;      // third-level candidates from which an item is processed by a whole warp
-constexpr int kHeavyCap = 1024;     // deferred heavy items per chunk
+constexpr int kHeavySplit = 4;       // warps per heavy item (x 32 lanes = 128 shares of its third-level candidates)
 
 template <int W>
 __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_constant__ CountParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    __shared__ int ticket, heavy_n, heavy_ticket;
-    __shared__ int heavy[kHeavyCap];
+    __shared__ int ticket;
     __shared__ int64_t sh_range[2];
 
     const GsnPlan &P = prm.plan;
@@ -123,8 +123,6 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
         sh_range[0] = prm.node_ptr[g_lo];
         sh_range[1] = prm.node_ptr[g_hi];
         ticket = 0;
-        heavy_n = 0;
-        heavy_ticket = 0;
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
@@ -203,26 +201,12 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
         if (it >= ns * parts) break;
         const int s = s0 + it / parts;
         if (prm.warp_items && weight(s) >= kHeavyItem) {
-            // deferred: after the light items, whole warps take the heavy ones and their lanes split the third level
-            if (it % parts == 0) {
-                const int at = atomicAdd(&heavy_n, 1);
-                if (at < kHeavyCap) heavy[at] = s;
-                else for (int q = 0; q < parts; ++q) process(s, q, parts);       // list full: run it here
-            }
+            // deferred to count_heavy_kernel: one CTA owns this chunk, but a heavy graph (IMDB-BINARY: 136 nodes, every
+            // edge in hundreds of K5) needs the whole machine, not four warps
+            if (it % parts == 0) prm.heavy[4 + atomicAdd(&prm.heavy[0], 1)] = s;
             continue;
         }
         process(s, it % parts, parts);
-    }
-    if (prm.warp_items) {
-        __syncthreads();
-        const int nh = heavy_n < kHeavyCap ? heavy_n : kHeavyCap;
-        const int lane = threadIdx.x & 31;
-        while (true) {
-            int k = lane == 0 ? atomicAdd(&heavy_ticket, 1) : 0;
-            k = __shfl_sync(0xffffffffu, k, 0);
-            if (k >= nh) break;
-            process(heavy[k], lane, 32);
-        }
     }
     if (!acc_in_smem) return;
     __syncthreads();
@@ -232,6 +216,28 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
     } else {
         uint32_t *dst = prm.slot_acc + (size_t)s0 * C;
         for (int i = threadIdx.x; i < ns * C; i += kCountThreads) dst[i] = sm_acc[i];
+    }
+}
+
+// Heavy items (deferred by count_kernel): every warp takes (item, share) tasks from a global ticket; the item's
+// third-level candidates are split 32 * kHeavySplit ways over lanes and warps, the graph is read from global memory (L2)
+// and the counts are added with atomics to the rows count_kernel has already written.
+template <int W>
+__global__ void __launch_bounds__(256) count_heavy_kernel(const __grid_constant__ CountParams prm) {
+    const GsnPlan &P = prm.plan;
+    const int lane = threadIdx.x & 31;
+    const int n_tasks = prm.heavy[0] * kHeavySplit;
+    while (true) {
+        int t = lane == 0 ? atomicAdd(&prm.heavy[1], 1) : 0;
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tasks) break;
+        const int s = prm.heavy[4 + t / kHeavySplit];
+        const int part = (t % kHeavySplit) * 32 + lane;
+        const int a = prm.slot_src[s], b = prm.slot_dst[s];
+        const int gb = prm.nbase[a];
+        GraphView<W> G{prm.adj + (size_t)gb * W, prm.rowptr + gb};
+        GlobalAcc acc{(unsigned long long *)(prm.out + P.col0), prm.out_ld, (int64_t)gb, prm.slot_acc, P.n_cols, prm.status};
+        run_item<W>(P, G, a - gb, b - gb, acc, part, 32 * kHeavySplit);
     }
 }
 
@@ -277,9 +283,15 @@ template <int W>
 int launch_count(const CountParams &prm, int64_t chunks, size_t smem, cudaStream_t stream) {
     // per launch (cheap): the attribute belongs to the current device
     GSN_CUDA_OK(cudaFuncSetAttribute(count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (prm.warp_items) GSN_CUDA_OK(cudaMemsetAsync(prm.heavy, 0, 16, stream));
     count_kernel<W><<<(unsigned)chunks, kCountThreads, smem, stream>>>(prm);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("count_kernel");
+    if (prm.warp_items) {
+        count_heavy_kernel<W><<<kNumSMs * 4, 256, 0, stream>>>(prm);
+        GSN_BUMP(1);
+        GSN_LAUNCH_OK("count_heavy_kernel");
+    }
     return GSN_OK;
 }
 
@@ -289,7 +301,9 @@ using namespace gsn;
 
 extern "C" int gsn_count_scratch_bytes(int64_t N, int64_t E, const GsnPlan *h_plan, size_t *bytes) {
     if (!h_plan || !bytes || N < 0 || E < 0) return GSN_E_INVALID;
-    *bytes = h_plan->scope == 1 ? align_up(sizeof(uint32_t) * (size_t)(2 * E + 4) * (size_t)h_plan->n_cols, 256) : 256;
+    // [per-slot accumulators (edge scope)] [deferred heavy items: count, ticket, 2E slots]
+    const size_t acc = h_plan->scope == 1 ? align_up(sizeof(uint32_t) * (size_t)(2 * E + 4) * (size_t)h_plan->n_cols, 256) : 0;
+    *bytes = acc + align_up(sizeof(int32_t) * (size_t)(2 * E + 8), 256);
     return GSN_OK;
 }
 
@@ -323,10 +337,12 @@ extern "C" int gsn_count_pattern(const void *d_ws, int64_t N, int64_t E, int32_t
     prm.slot_acc = (uint32_t *)d_scratch;
     prm.status = d_status;
     prm.plan = P;
-    if (P.scope == 1) {
+    {
         size_t need = 0;
         gsn_count_scratch_bytes(N, E, h_plan, &need);
         if (!d_scratch || scratch_bytes < need) return GSN_E_WORKSPACE;
+        const size_t acc = P.scope == 1 ? align_up(sizeof(uint32_t) * (size_t)(2 * E + 4) * (size_t)P.n_cols, 256) : 0;
+        prm.heavy = (int32_t *)((char *)d_scratch + acc);
     }
 
     // chunking: enough CTAs to cover the machine several times, enough items per CTA to fill it
