@@ -42,5 +42,34 @@ ef = ids[:, :4].float()
 y = directional.dgn_aggregate(plan, h, ids_v[:, :2].float(), ef, 'mean max min std dir0-av dir1-dx dir5-0.1 dir2-dx-balanced',
                               'identity amplification', {'log': 1.1})
 y.square().sum().backward()
+# ---- round 2: general COUNT path (graph build + count + heavy-item kernel) on a dense batch, one-launch COUNT (above),
+#      one-kernel forward through the pipeline, training kernels (embedding bag fwd/bwd, ogb fwd/bwd, tensor-core Linear)
+from tests.util import batch_graphs, random_graph
+rng = np.random.default_rng(0)
+gs = [(random_graph(rng, 30, 0.6), 30) for _ in range(4)] + [(random_graph(rng, 70, 0.3), 70)]
+dptr, _, dei = batch_graphs(gs)
+import networkx as nx
+cl = patterns.make_subgraph_dicts([list(nx.complete_graph(k).edges) for k in (3, 4, 5)], 'local')
+counting.count_batch(torch.from_numpy(dei).to(dev), torch.from_numpy(dptr), cl, False, 'local')
+from gsn_b200.network import GNNSubstructures
+from gsn_b200.pipeline import BucketedPipeline, GSNPipeline, UniqueEncoder
+enc = UniqueEncoder.fit(ids)
+torch.manual_seed(0)
+with contextlib.redirect_stdout(io.StringIO()):
+    model = GNNSubstructures(**bench.model_ctor(enc.d), **bench.model_args(enc.d)).to(dev).eval()
+t = bench.to_tensors(b, device=dev)
+with torch.no_grad():
+    o1 = GSNPipeline(model, sds, False, 'local', enc, 64, fused='model').step(t)
+bp = BucketedPipeline(model, sds, False, 'local', enc, 64)
+key, packed, G = bp.prepare(b, dev)
+o2 = bp.run(key, packed, G)
+tabs = [torch.randn((v, 300), device=dev, requires_grad=True) for v in (64, 5, 2, 119)]
+idx = torch.stack([torch.randint(0, v, (N,), device=dev) for v in (64, 5, 2, 119)], 1)
+eb = ops.embedding_bag(idx, tabs)
+xx = torch.randn((N, 300), device=dev, requires_grad=True)
+eff = torch.randn((E, 300), device=dev, requires_grad=True)
+agg = ops.ogb_aggregate_ad(ei, N, 'source_to_target', xx, eb, False, eff, torch.zeros(1, device=dev))
+lin = torch.nn.Linear(300, 600).to(dev)
+(ops.linear_ad(agg.repeat(8, 1), lin.weight, lin.bias).square().sum()).backward()
 torch.cuda.synchronize()
-print('sanitize: all kernels ran', float(y.sum()), float(h.grad.abs().sum()))
+print('sanitize: all kernels ran', float(y.sum()), float(h.grad.abs().sum()), float((o1 - o2).abs().max()), float(xx.grad.abs().sum()))

@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests.tolerance import FWD, GRAD, close
+
 from oracle import dgn_ref
 from tests.conftest import GOLDEN
 
@@ -33,7 +35,7 @@ def test_aggregate_and_layer_vs_reference_golden(name):
     torch.backends.cuda.matmul.allow_tf32 = False
     with torch.no_grad():
         y = layer(g, c['h'].cuda(), None, c['snorm_n'].cuda())
-    torch.testing.assert_close(y.cpu(), c['out'], atol=2e-5, rtol=1e-5)
+    close(y, c['out'])
 
 
 def test_count_fields_feed_the_aggregation_zinc_sized():
@@ -95,7 +97,7 @@ def test_aggregate_backward_vs_reference_autograd(name):
     h = c['h'].cuda().requires_grad_(True)
     agg = directional.dgn_aggregate(g.plan, h, g.ndata_eig, g.edata_eig, c['aggregators'], c['scalers'], c['avg_d'])
     (agg * c['cot'].cuda()).sum().backward()
-    torch.testing.assert_close(h.grad.cpu(), c['h_grad'], atol=2e-5, rtol=1e-5)
+    close(h.grad, c['h_grad'], GRAD)
 
 
 def test_layer_training_step_gradients_vs_oracle():
@@ -120,10 +122,10 @@ def test_layer_training_step_gradients_vs_oracle():
     h1 = c['h'].cuda().requires_grad_(True)
     y1 = layer(g, h1, None, None)
     (y1 ** 2).mean().backward()
-    torch.testing.assert_close(y1.detach().cpu(), y0.detach(), atol=2e-5, rtol=1e-5)
-    torch.testing.assert_close(h1.grad.cpu(), h0.grad, atol=2e-5, rtol=1e-4)
+    close(y1, y0)
+    close(h1.grad, h0.grad, GRAD)
     for (k, p1), (_, p0) in zip(layer.named_parameters(), ref.named_parameters()):
-        torch.testing.assert_close(p1.grad.cpu(), p0.grad, atol=2e-5, rtol=1e-4, msg=lambda m, k=k: f'{k}: {m}')
+        close(p1.grad, p0.grad, GRAD, msg=k)
 
 
 def test_dgn_net_forward_matches_layerwise_oracle():
@@ -156,4 +158,4 @@ def test_dgn_net_forward_matches_layerwise_oracle():
     g = directional.DirectionalBatch(ei.cuda(), N, node_ptr=node_ptr.cuda(), edata_eig=ef.cuda())
     with torch.no_grad():
         got = net(g, x.cuda(), None)
-    torch.testing.assert_close(got.cpu(), exp, atol=2e-5, rtol=1e-5)
+    close(got, exp)

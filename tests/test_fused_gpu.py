@@ -6,6 +6,8 @@ import os
 import pytest
 import torch
 
+from tests.tolerance import FWD, GRAD, close
+
 from oracle import mp_ref
 from tests.conftest import GOLDEN
 from tests.test_oracle_mp import model_layer_cfgs
@@ -38,12 +40,12 @@ def test_linear_kernel_vs_torch(M, K1, K2, Nout, mode, monkeypatch):
     c = lambda t: None if t is None else t.cuda()
     out = ops.linear(c(A1), c(W), bias=c(bias), A2=c(A2), row_scale=c(rs), row_vec=c(rv), tab_idx=c(tidx), tab=c(tab),
                      scale=c(scale), shift=c(shift), activation='relu')
-    torch.testing.assert_close(out.cpu(), ref, atol=2e-5, rtol=1e-5)
+    close(out, ref)
     out2 = ops.linear(c(A1), c(W), A2=c(A2), activation='identity')
-    torch.testing.assert_close(out2.cpu(), (A.double() @ W.double().t()).float(), atol=2e-5, rtol=1e-5)
+    close(out2, (A.double() @ W.double().t()).float())
     acc = out2.clone()
     ops.linear(c(A1), c(W), A2=c(A2), out=acc, accumulate=True)
-    torch.testing.assert_close(acc, 2 * out2, atol=1e-5, rtol=1e-5)
+    close(acc, 2 * out2)
 
 
 def test_pool_ptr_and_encode_rows():
@@ -95,7 +97,7 @@ def test_fused_forward_matches_reference_output(name):
     G = int(c['data']['batch'].max()) + 1
     b.node_ptr = torch.searchsorted(c['data']['batch'], torch.arange(G + 1)).cuda()
     out = fused.FusedForward(model)(b)
-    torch.testing.assert_close(out.cpu(), c['out'], atol=2e-5, rtol=2e-5)
+    close(out, c['out'])
 
 
 def test_fused_pipeline_vs_generic_pipeline_and_oracle():
@@ -139,5 +141,5 @@ def test_fused_pipeline_vs_generic_pipeline_and_oracle():
     sd = {k: v.cpu() for k, v in model.state_dict().items()}
     ref = mp_ref.gnn_substructures_forward(args, sd, data, model_layer_cfgs(args))
     scale = float(ref.abs().max())
-    torch.testing.assert_close(out_g.cpu(), ref, atol=1e-5 * max(scale, 1), rtol=1e-5)
-    torch.testing.assert_close(out_f.cpu(), ref, atol=1e-5 * max(scale, 1), rtol=1e-5)
+    close(out_g, ref)
+    close(out_f, ref)

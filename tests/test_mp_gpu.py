@@ -1,6 +1,6 @@
 """MP parity: CUDA layers (through the C ABI) vs the reference's own outputs
 (tests/golden/mp_*.pt) and vs the fp32 CPU oracle (oracle/mp_ref.py).
-Tolerance: atol = rtol = 1e-5 in fp32 (BASELINE.json north_star)."""
+Tolerance: tests/tolerance.py (1e-5 relative to the scale of the compared tensor; BASELINE.json north_star)."""
 import contextlib
 import io
 import os
@@ -8,6 +8,8 @@ import os
 import numpy as np
 import pytest
 import torch
+
+from tests.tolerance import FWD, GRAD, close
 
 from oracle import mp_ref
 from tests.conftest import GOLDEN
@@ -75,21 +77,21 @@ def test_layer_training_mode_and_gradients(name):
     g = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in leaves.items()}
     out = layer(g['x'], inp['edge_index'].cuda(), identifiers=g.get('identifiers', None if inp['identifiers'] is None else inp['identifiers'].cuda()),
                 degrees=inp['degrees'].cuda(), edge_features=g.get('edge_features'))
-    torch.testing.assert_close(out.detach().cpu(), ref.detach(), atol=2e-5, rtol=2e-5)
+    close(out, ref)
     (out * w.cuda()).sum().backward()
     for k in leaves:
         if kw.get('degree_as_tag') and not kw.get('retain_features') and k == 'x':
             continue
-        torch.testing.assert_close(g[k].grad.cpu(), leaves[k].grad, atol=5e-5, rtol=5e-5)
+        close(g[k].grad, leaves[k].grad, GRAD, msg=k)
     for pname, p in layer.named_parameters():
         if sd[pname].grad is not None:
-            torch.testing.assert_close(p.grad.cpu(), sd[pname].grad, atol=1e-4, rtol=1e-4)
+            close(p.grad, sd[pname].grad, GRAD, msg=pname)
     # no-grad training-mode forward (fused kernels with batch statistics) agrees as well
     layer.load_state_dict(c['state_dict'], strict=True)
     with torch.no_grad():
         out_ng = layer(g['x'].detach(), inp['edge_index'].cuda(), identifiers=None if inp['identifiers'] is None else inp['identifiers'].cuda(),
                        degrees=inp['degrees'].cuda(), edge_features=None if inp.get('edge_features') is None else inp['edge_features'].cuda())
-    torch.testing.assert_close(out_ng.cpu(), ref.detach(), atol=2e-5, rtol=2e-5)
+    close(out_ng, ref)
 
 
 @pytest.mark.parametrize('name', list(MODEL_GOLDEN))
@@ -108,7 +110,7 @@ def test_model_matches_reference_output(name):
         setattr(b, k, v.cuda())
     with torch.no_grad():
         out = model(b)
-    torch.testing.assert_close(out.cpu(), c['out'], atol=2e-5, rtol=2e-5)
+    close(out, c['out'])
 
 
 @pytest.mark.parametrize('name', ['gsne_general_local', 'gsne_general_global', 'gsn_gin_local_onehot', 'gsn_ogb_local',
@@ -149,7 +151,7 @@ def test_layer_vs_oracle_zinc_sized_batch(name):
     # outputs are O(1); 1e-5 relative to the layer's output scale
     scale = float(ref.abs().max())
     assert float((out.cpu() - ref).abs().max()) <= 1e-5 * max(scale, 1.0) + 1e-5 * 0
-    torch.testing.assert_close(out.cpu(), ref, atol=1e-5 * max(scale, 1.0), rtol=1e-5)
+    close(out, ref)
 
 
 def test_edge_plan_rows_are_sorted_and_complete():

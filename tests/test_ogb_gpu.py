@@ -8,6 +8,8 @@ import os
 import pytest
 import torch
 
+from tests.tolerance import FWD, GRAD, close
+
 from tests.conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
@@ -37,7 +39,7 @@ def test_gnn_ogb_eval_forward(name):
     m = _model(c).eval()
     with torch.no_grad():
         y = m(_batch(c))
-    torch.testing.assert_close(y.cpu(), c['y_eval'], atol=2e-5, rtol=2e-5)
+    close(y, c['y_eval'])
 
 
 @pytest.mark.parametrize('name', [n for n in OGB if 'grads' in OGB[n]])
@@ -45,14 +47,14 @@ def test_gnn_ogb_train_step_gradients(name):
     c = OGB[name]
     m = _model(c).train()
     y = m(_batch(c))
-    torch.testing.assert_close(y.detach().cpu(), c['y_train'], atol=2e-5, rtol=2e-5)
+    close(y, c['y_train'])
     loss = torch.nn.functional.binary_cross_entropy_with_logits(y, c['target'].cuda())
-    torch.testing.assert_close(loss.detach().cpu(), c['loss'], atol=1e-5, rtol=1e-5)
+    close(loss, c['loss'])
     loss.backward()
     got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
     assert set(got) == set(c['grads'])
     for k, gref in c['grads'].items():
-        torch.testing.assert_close(got[k].cpu(), gref, atol=2e-5, rtol=1e-4, msg=lambda s, k=k: f'{k}: {s}')
+        close(got[k], gref, GRAD, msg=k)
     # one optimiser step runs end to end
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
     opt.step()
