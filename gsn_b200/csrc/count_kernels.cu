@@ -98,7 +98,7 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t n, 
 }
 
 constexpr int kCountThreads = 128;
-constexpr int kHeavyItem = 24;      // third-level candidates from which an item is processed by a whole warp
+constexpr int kHeavyItem = 12;      // third-level candidates from which an item is deferred to count_heavy_kernel
 constexpr int kHeavySplit = 4;       // warps per heavy item (x 32 lanes = 128 shares of its third-level candidates)
 
 template <int W>
@@ -224,9 +224,17 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
 // and the counts are added with atomics to the rows count_kernel has already written.
 template <int W>
 __global__ void __launch_bounds__(256) count_heavy_kernel(const __grid_constant__ CountParams prm) {
+    // per warp: the adjacency rows and slot offsets of the graph its current task belongs to (W <= 4: <= 256 vertices,
+    // 9 KB); the search does one dependent adjacency read per search node, from L2 that was the whole cost of a task
+    extern __shared__ __align__(16) unsigned char hv_smem[];
+    constexpr int MAXN = 64 * W;
+    constexpr bool STAGE = W <= 4;
     const GsnPlan &P = prm.plan;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t *wadj = (uint64_t *)hv_smem + (size_t)warp * MAXN * W;
+    int32_t *wrow = (int32_t *)(hv_smem + (size_t)8 * MAXN * W * 8) + (size_t)warp * (MAXN + 4);
     const int n_tasks = prm.heavy[0] * kHeavySplit;
+    int staged = -1;
     while (true) {
         int t = lane == 0 ? atomicAdd(&prm.heavy[1], 1) : 0;
         t = __shfl_sync(0xffffffffu, t, 0);
@@ -235,7 +243,15 @@ __global__ void __launch_bounds__(256) count_heavy_kernel(const __grid_constant_
         const int part = (t % kHeavySplit) * 32 + lane;
         const int a = prm.slot_src[s], b = prm.slot_dst[s];
         const int gb = prm.nbase[a];
-        GraphView<W> G{prm.adj + (size_t)gb * W, prm.rowptr + gb};
+        if (STAGE && gb != staged) {
+            __syncwarp();
+            const int n = (int)min((int64_t)MAXN, prm.N - gb);
+            for (int i = lane; i < n * W; i += 32) wadj[i] = prm.adj[(size_t)gb * W + i];
+            for (int i = lane; i <= n; i += 32) wrow[i] = prm.rowptr[gb + i];
+            staged = gb;
+            __syncwarp();
+        }
+        GraphView<W> G{STAGE ? wadj : prm.adj + (size_t)gb * W, STAGE ? wrow : prm.rowptr + gb};
         GlobalAcc acc{(unsigned long long *)(prm.out + P.col0), prm.out_ld, (int64_t)gb, prm.slot_acc, P.n_cols, prm.status};
         run_item<W>(P, G, a - gb, b - gb, acc, part, 32 * kHeavySplit);
     }
@@ -288,7 +304,9 @@ int launch_count(const CountParams &prm, int64_t chunks, size_t smem, cudaStream
     GSN_BUMP(1);
     GSN_LAUNCH_OK("count_kernel");
     if (prm.warp_items) {
-        count_heavy_kernel<W><<<kNumSMs * 4, 256, 0, stream>>>(prm);
+        const size_t hsm = W <= 4 ? (size_t)8 * (64 * W * W * 8 + (64 * W + 4) * 4) : 0;
+        GSN_CUDA_OK(cudaFuncSetAttribute(count_heavy_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        count_heavy_kernel<W><<<kNumSMs * 2, 256, hsm, stream>>>(prm);
         GSN_BUMP(1);
         GSN_LAUNCH_OK("count_heavy_kernel");
     }
