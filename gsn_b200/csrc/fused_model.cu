@@ -260,7 +260,7 @@ struct FmCfg {
     static constexpr int OFF_TE = OFF_RING + NST * STAGE;
     static constexpr int OFF_VEC = OFF_TE + FM_TE_SMALL;
     static constexpr int OFF_RMAX = OFF_VEC + VEC_BYTES;
-    static constexpr int SMEM = OFF_RMAX + FM_NPART * FM_ROWS * 4 + 1024;     // + alignment slack
+    static constexpr int SMEM = OFF_RMAX + 2 * FM_NPART * FM_ROWS * 4 + 1024;     // two row-max buffers + alignment slack
     static constexpr int CW = D / FM_NPART;                 // columns per compute thread (FM_NPART threads share a row)
     static constexpr uint32_t TMEM_COLS = 4 * D;            // acc0 (main|corr) | acc1 (main|corr)
 };
@@ -444,14 +444,19 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
         // visible to the tensor core and signals the MMA warp.  `live` = the warp holds at least one valid row (other
         // warps only take part in the barriers: their operand rows are never read back -- row i of a product depends on
         // row i of the operand alone).
+        // The partial maxima alternate between two buffers: a warp that runs ahead into the next call writes the other
+        // buffer, and the one after that is ordered behind this call's reads by the next call's barrier.
+        uint32_t n_operand = 0;
         auto finish_operand = [&](float m, bool live) -> float {
-            if (live) rmax[part * FM_ROWS + r] = m;
+            float *rm = rmax + (n_operand & 1) * (FM_NPART * FM_ROWS);
+            ++n_operand;
+            if (live) rm[part * FM_ROWS + r] = m;
             fm_bar_compute();
             float inv = 1.f;
             if (live) {
-                m = rmax[r];
+                m = rm[r];
 #pragma unroll
-                for (int pp = 1; pp < FM_NPART; ++pp) m = fmaxf(m, rmax[pp * FM_ROWS + r]);
+                for (int pp = 1; pp < FM_NPART; ++pp) m = fmaxf(m, rm[pp * FM_ROWS + r]);
                 int e = (int)((__float_as_uint(m) >> 23) & 0xFF);                 // biased exponent of the row maximum
                 if (e == 0) e = 127 + 14;                                          // zero / denormal row: scale 1
                 int se = 127 + 14 - (e - 127);                                     // scale = 2^(14 - (e - 127))
