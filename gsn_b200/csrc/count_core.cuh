@@ -69,6 +69,12 @@ struct VSet {
         for (int i = 0; i < W; ++i) c += popc64(w[i]);
         return c;
     }
+    GSN_HD int count_and(const uint64_t *p) const {          // |this & p|
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) c += popc64(w[i] & p[i]);
+        return c;
+    }
     GSN_HD void and_with(const uint64_t *p) {
 #pragma unroll
         for (int i = 0; i < W; ++i) w[i] &= p[i];
@@ -141,11 +147,14 @@ GSN_HD int rank_below(const uint64_t *p, int b) {
 
 // One graph as the kernels see it: adjacency rows of W words per LOCAL vertex id
 // and the slot offset of every local vertex (CSR of the simple graph).
+// `stride` (words between rows) may exceed W: a graph of <= 64 * W vertices inside a batch laid out for wider graphs
+// is searched with W-word sets (its rows are zero beyond word W).
 template <int W>
 struct GraphView {
-    const uint64_t *adj;     // adj + v*W
+    const uint64_t *adj;     // adj + v*stride
     const int32_t *rowptr;   // rowptr[v] = first slot of local vertex v (batch-global slot ids)
-    GSN_HD const uint64_t *row(int v) const { return adj + (size_t)v * W; }
+    int32_t stride = W;
+    GSN_HD const uint64_t *row(int v) const { return adj + (size_t)v * stride; }
     GSN_HD int slot(int a, int b) const { return rowptr[a] + rank_below<W>(row(a), b); }
 };
 
@@ -335,62 +344,65 @@ GSN_HD void enumerate_cycles(int kmin, int kmax, int induced, int scope, const G
 }
 
 // ------------------------------------------------------------------- cliques
-// All clique sizes kmin..kmax in one traversal over increasing vertex tuples
-// (one representative of the k! maps).  column = size - kmin.
+// All clique sizes kmin..kmax of one item, counted LOCALLY: the number of k-cliques through the edge {a,b} is the
+// number of (k-2)-cliques inside the common neighbourhood N(a) & N(b), so an item owns its result and adds it once --
+// no update per occurrence, no slot lookup per occurrence.  The search runs over increasing vertex tuples inside that
+// set (one representative of the (k-2)! orders) and the last level is a population count.  column = size - kmin.
+//   edge scope:   item (a,b), a < b, pool = N(a) & N(b); both slots of the edge receive the totals.
+//   vertex scope: item (a,b), every direction, pool = N(a) & N(b) & {> b}: the cliques through a whose smallest other
+//                 member is b; vertex a receives the totals (summed over b: every clique through a exactly once).
 template <int W, class Acc>
 GSN_HD void enumerate_cliques(int kmin, int kmax, int scope, const GraphView<W> &G, int a, int b, Acc &acc,
                               int part = 0, int parts = 1) {
-    if (b <= a) return;
-    int f[GSN_MAXK];
+    if (scope != 0 && b <= a) return;
     VSet<W> cand[GSN_MAXK];
-    f[0] = a;
-    f[1] = b;
+    uint64_t total[GSN_MAXK + 1];
+#pragma unroll
+    for (int i = 0; i <= GSN_MAXK; ++i) total[i] = 0;
     cand[2].load(G.row(a));
     cand[2].and_with(G.row(b));
-    cand[2].keep_gt(b);
-    const VSet<W> pool2 = cand[2];           // every common neighbour > b: the pool deeper levels draw from
-    keep_part<W>(cand[2], part, parts);      // each sub-item records and extends its own share of the triangles
+    if (scope == 0) cand[2].keep_gt(b);
+    const VSet<W> pool = cand[2];            // deeper levels draw from the whole pool
+    keep_part<W>(cand[2], part, parts);      // each sub-item counts and extends its own share of the triangles
     int p = 2;
-    bool fresh = true;   // cand[p] was just computed: record the (p+1)-cliques it closes
+    bool fresh = true;   // cand[p] was just computed: it closes cand[p].count() cliques of size p+1
     while (true) {
         if (fresh) {
             fresh = false;
-            int size = p + 1;
-            if (size >= kmin && size <= kmax) {
+            const int size = p + 1;
+            if (size >= kmin && size <= kmax) total[size] += (uint64_t)cand[p].count();
+            if (size >= kmax) {
+                cand[p].clear();                 // no deeper level needed
+            } else if (size + 1 == kmax) {
+                // the next level is the last: every j of cand[p] closes |candidates after j that are adjacent to j|
+                // cliques of size kmax -- counted here, without a visit per (j, candidate set)
+                uint64_t c = 0;
                 VSet<W> t = cand[p];
-                uint32_t c = (uint32_t)t.count();
-                int col = size - kmin;
-                if (c) {
-                    if (scope == 0) {
-                        for (int q = 0; q < p; ++q) acc.vertex(f[q], col, c);
-                        while (!t.empty()) acc.vertex(t.pop_lowest(), col, 1u);
-                    } else {
-                        for (int q = 0; q < p; ++q)
-                            for (int r = 0; r < q; ++r) {
-                                acc.slot(G.slot(f[r], f[q]), col, c);
-                                acc.slot(G.slot(f[q], f[r]), col, c);
-                            }
-                        while (!t.empty()) {
-                            int j = t.pop_lowest();
-                            for (int q = 0; q < p; ++q) {
-                                acc.slot(G.slot(f[q], j), col, 1u);
-                                acc.slot(G.slot(j, f[q]), col, 1u);
-                            }
-                        }
+                if (p == 2 && parts > 1) {
+                    while (!t.empty()) {
+                        const int j = t.pop_lowest();
+                        VSet<W> u = pool;
+                        u.keep_gt(j);
+                        c += (uint64_t)u.count_and(G.row(j));
+                    }
+                } else {
+                    while (!t.empty()) {
+                        const int j = t.pop_lowest();    // ascending: what is left in t is > j
+                        c += (uint64_t)t.count_and(G.row(j));
                     }
                 }
+                total[kmax] += c;
+                cand[p].clear();
             }
-            if (size >= kmax) cand[p].clear();   // no deeper level needed
         }
         if (cand[p].empty()) {
             if (p == 2) break;
             --p;
             continue;
         }
-        int j = cand[p].pop_lowest();
-        f[p] = j;
-        if (p == 2) {                   // the sub-item filter applies to the choice of f[2] only
-            cand[3] = pool2;
+        const int j = cand[p].pop_lowest();
+        if (p == 2) {                   // the sub-item filter applies to the first choice only
+            cand[3] = pool;
             cand[3].keep_gt(j);
         } else {
             cand[p + 1] = cand[p];      // remaining candidates are all > j already (ascending pop)
@@ -398,6 +410,21 @@ GSN_HD void enumerate_cliques(int kmin, int kmax, int scope, const GraphView<W> 
         cand[p + 1].and_with(G.row(j));
         ++p;
         fresh = true;
+    }
+    int s_ab = -1, s_ba = -1;
+    for (int size = kmin; size <= kmax; ++size) {
+        if (total[size] == 0) continue;
+        const uint32_t c = clamp32(total[size], acc);
+        if (scope == 0) {
+            acc.vertex(a, size - kmin, c);
+        } else {
+            if (s_ab < 0) {
+                s_ab = G.slot(a, b);
+                s_ba = G.slot(b, a);
+            }
+            acc.slot(s_ab, size - kmin, c);
+            acc.slot(s_ba, size - kmin, c);
+        }
     }
 }
 

@@ -99,6 +99,9 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t n, 
 
 constexpr int kCountThreads = 128;
 constexpr int kHeavyItem = 12;      // third-level candidates from which an item is deferred to count_heavy_kernel
+constexpr int kHeavyClique = 8;     // same for cliques (an item counts inside its pool of common neighbours); a heavy clique item is
+                                    // one warp's task, the lanes take the pool's vertices as first choices
+constexpr int kHeavyBatch = 4;       // consecutive tasks per ticket
 constexpr int kHeavySplit = 4;       // warps per heavy item (x 32 lanes = 128 shares of its third-level candidates)
 
 template <int W>
@@ -174,13 +177,18 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
         const int a = prm.slot_src[s], b = prm.slot_dst[s];
         const int gb = prm.nbase[a];                      // first node of the graph
         const int off = (int)(gb - v0);
+        // a graph of <= 64 vertices inside a batch laid out for wider ones (node gb + 64 is not its own): one-word sets
+        const bool narrow = W > 1 && (gb + 64 >= prm.N || prm.nbase[gb + 64] != gb);
         GraphView<W> G{adj_base + (size_t)off * W, row_base + off};
+        GraphView<1> G1{adj_base + (size_t)off * W, row_base + off, W};
         if (acc_in_smem) {
             SmemAcc acc{sm_acc, C, off, s0, prm.status};
-            run_item<W>(P, G, a - gb, b - gb, acc, part, nparts);
+            if (narrow) run_item<1>(P, G1, a - gb, b - gb, acc, part, nparts);
+            else run_item<W>(P, G, a - gb, b - gb, acc, part, nparts);
         } else {
             GlobalAcc acc{(unsigned long long *)(prm.out + P.col0), prm.out_ld, (int64_t)gb, prm.slot_acc, C, prm.status};
-            run_item<W>(P, G, a - gb, b - gb, acc, part, nparts);
+            if (narrow) run_item<1>(P, G1, a - gb, b - gb, acc, part, nparts);
+            else run_item<W>(P, G, a - gb, b - gb, acc, part, nparts);
         }
     };
     // how many third-level candidates an item has (cliques: common neighbours; otherwise the degree of b): an item
@@ -190,17 +198,19 @@ __global__ void __launch_bounds__(kCountThreads) count_kernel(const __grid_const
         const int a = prm.slot_src[s], b = prm.slot_dst[s];
         const int gb = prm.nbase[a];
         const uint64_t *ra = adj_base + (size_t)(a - v0) * W, *rb = adj_base + (size_t)(b - v0) * W;
+        (void)gb;
+        if (P.family == GSN_FAMILY_CLIQUES && P.scope != 0 && b <= a) return 0;     // the a < b item counts for both slots
         int c = 0;
         for (int i = 0; i < W; ++i) c += __popcll(P.family == GSN_FAMILY_CLIQUES ? (ra[i] & rb[i]) : rb[i]);
-        (void)gb;
         return c;
     };
+    const int heavy_min = P.family == GSN_FAMILY_CLIQUES ? kHeavyClique : kHeavyItem;
     const int parts = prm.parts;
     while (true) {
         const int it = atomicAdd(&ticket, 1);
         if (it >= ns * parts) break;
         const int s = s0 + it / parts;
-        if (prm.warp_items && weight(s) >= kHeavyItem) {
+        if (prm.warp_items && weight(s) >= heavy_min) {
             // deferred to count_heavy_kernel: one CTA owns this chunk, but a heavy graph (IMDB-BINARY: 136 nodes, every
             // edge in hundreds of K5) needs the whole machine, not four warps
             if (it % parts == 0) prm.heavy[4 + atomicAdd(&prm.heavy[0], 1)] = s;
@@ -233,27 +243,43 @@ __global__ void __launch_bounds__(256) count_heavy_kernel(const __grid_constant_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t *wadj = (uint64_t *)hv_smem + (size_t)warp * MAXN * W;
     int32_t *wrow = (int32_t *)(hv_smem + (size_t)8 * MAXN * W * 8) + (size_t)warp * (MAXN + 4);
-    const int n_tasks = prm.heavy[0] * kHeavySplit;
+    const int split = P.family == GSN_FAMILY_CLIQUES ? 1 : kHeavySplit;
+    const int batch = P.family == GSN_FAMILY_CLIQUES ? kHeavyBatch : 1;      // the shares of a split item go to different warps
+    const int n_tasks = prm.heavy[0] * split;
     int staged = -1;
+    // tickets are taken kHeavyBatch at a time: neighbouring entries of the list mostly come from one graph (one chunk
+    // of count_kernel pushed them), so the staged copy is reused and the ticket's round trip is shared
+    int t_next = 0, t_end = 0;
     while (true) {
-        int t = lane == 0 ? atomicAdd(&prm.heavy[1], 1) : 0;
-        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t_next == t_end) {
+            t_next = lane == 0 ? atomicAdd(&prm.heavy[1], batch) : 0;
+            t_next = __shfl_sync(0xffffffffu, t_next, 0);
+            t_end = t_next + batch;
+        }
+        const int t = t_next++;
         if (t >= n_tasks) break;
-        const int s = prm.heavy[4 + t / kHeavySplit];
-        const int part = (t % kHeavySplit) * 32 + lane;
+        const int s = prm.heavy[4 + t / split];
+        const int part = (t % split) * 32 + lane;
         const int a = prm.slot_src[s], b = prm.slot_dst[s];
         const int gb = prm.nbase[a];
         if (STAGE && gb != staged) {
             __syncwarp();
-            const int n = (int)min((int64_t)MAXN, prm.N - gb);
+            // upper bound on the graph's size from 32 probes of the node -> first-node map
+            constexpr int STEP = MAXN / 32;
+            const int64_t probe = (int64_t)gb + STEP * (lane + 1);
+            const unsigned past = __ballot_sync(0xffffffffu, probe >= prm.N || prm.nbase[probe] != gb);
+            const int n = (int)min((int64_t)(past ? STEP * __ffs(past) : MAXN), prm.N - gb);
             for (int i = lane; i < n * W; i += 32) wadj[i] = prm.adj[(size_t)gb * W + i];
             for (int i = lane; i <= n; i += 32) wrow[i] = prm.rowptr[gb + i];
             staged = gb;
             __syncwarp();
         }
+        const bool narrow = W > 1 && (gb + 64 >= prm.N || prm.nbase[gb + 64] != gb);       // see count_kernel
         GraphView<W> G{STAGE ? wadj : prm.adj + (size_t)gb * W, STAGE ? wrow : prm.rowptr + gb};
+        GraphView<1> G1{G.adj, G.rowptr, W};
         GlobalAcc acc{(unsigned long long *)(prm.out + P.col0), prm.out_ld, (int64_t)gb, prm.slot_acc, P.n_cols, prm.status};
-        run_item<W>(P, G, a - gb, b - gb, acc, part, 32 * kHeavySplit);
+        if (narrow) run_item<1>(P, G1, a - gb, b - gb, acc, part, 32 * split);
+        else run_item<W>(P, G, a - gb, b - gb, acc, part, 32 * split);
     }
 }
 
