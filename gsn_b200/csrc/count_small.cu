@@ -511,7 +511,11 @@ extern "C" int gsn_count_small(const int64_t *d_edge_index, int64_t E, const int
     if (T > t_fill) T = t_fill;
     if (T < 48) T = 48;              // >= ~2 molecules per CTA: a chunk pays its set-up (searches, scan) once
     if (T > 1024) T = 1024;
-    const bool small_batch = ceil_div(N, T) <= 2 * kNumSMs;
+    // a batch that fits one wave of CTAs at ~one molecule each (B = 128): the step waits for the slowest CTA, so the
+    // roots of a molecule are spread over eight warps instead of two molecules over four
+    const bool one_wave = ceil_div(N, 24) <= kNumSMs;
+    if (one_wave) T = 24;
+    const bool small_batch = !one_wave && ceil_div(N, T) <= 2 * kNumSMs;
     const int NT = small_batch ? 128 : 256;
     CsParams prm;
     prm.src = d_edge_index; prm.dst = d_edge_index ? d_edge_index + E : nullptr; prm.E = E;
