@@ -262,10 +262,14 @@ def run_ours(args, rank, world, local_rank):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         run_steps(args.steps, args.warmup, src, d2h)
+        host_enqueue_us.append((time.perf_counter() - t_host) * 1e6 / args.steps)
         e1.record()
         barrier()
         return e0.elapsed_time(e1)
+
+    host_enqueue_us = []       # host time to enqueue one step (copy + graph launch), per timed region
 
     with Clocks(local_rank) as clk:
         # ---- single stream, one step at a time, L2 flushed before every step, a different batch every step: the latency
@@ -429,6 +433,8 @@ def run_ours(args, rank, world, local_rank):
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(my_launches_per_step) * args.steps,     # our kernels; + 1 packed input copy per step
             'gpu_launches_per_step': int(my_launches_per_step),
+            'host_enqueue_us_per_step': {'value': host_enqueue_us[0], 'e2e': host_enqueue_us[1],
+                                         'note': 'host time to enqueue a step (packed copy + graph launch) in the two timed regions'},
             'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep,
             'scatter_kernels': scatter_kernels, 'roofline_large_batch': roof_large, 'torch_eager_gpu': eager, 'gsn_v': gsn_v,
         }
@@ -686,9 +692,13 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=128)
     ap.add_argument('--no-sweep', action='store_true')
+    ap.add_argument('--fill-rows', type=float, default=None, help='experiment: gsn_b200.fused_model.FILL_ROWS')
     ap.add_argument('--streams', type=int, default=8, help='independent steps in flight (CUDA streams / captured graphs)')
     ap.add_argument('--pool', type=int, default=640, help='distinct same-shape input batches cycled through (> L2 in total)')
     args = ap.parse_args()
+    if args.fill_rows is not None and args.impl == 'ours':
+        from gsn_b200 import fused_model as _fm
+        _fm.FILL_ROWS = float(args.fill_rows)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

@@ -56,6 +56,7 @@ struct FmParams {
     const float *x0;
     int32_t x0_ld, x0_d;
     int32_t G, unit, n_units;
+    const int32_t *tile_plan;     // optional: { n_tiles, first graph of every tile, G }
     int32_t *status;
 };
 
@@ -275,6 +276,9 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the grid of a planned launch is the plan's CAPACITY (fixed when the step is captured): CTAs past the tile count leave
+    // before they allocate anything
+    if (P.tile_plan && (int)blockIdx.x >= P.tile_plan[0]) return;
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sA = smem_u32(sm + C::OFF_A), sPJ = smem_u32(sm + C::OFF_PJ), sRING = smem_u32(sm + C::OFF_RING);
     const uint32_t sTE = smem_u32(sm + C::OFF_TE);
@@ -308,13 +312,16 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
     const uint32_t tmem = tmem_base_smem;
     const uint32_t ACC0 = tmem, ACC1 = tmem + 2 * D;
     const int nL = P.n_layers;
+    // units of work: tiles of the plan (small batches: one CTA per tile) or runs of P.unit graphs cut into tiles here
+    const int32_t *tplan = P.tile_plan;
+    const int n_units = tplan ? tplan[0] : P.n_units;
 
     if (warp == 0) {
         // ------------------------------------------------------------- TMA producer: weight k-slabs in order of use
         uint32_t it = 0;
-        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
-            const int gend = min(P.G, (u + 1) * P.unit);
-            int g0 = u * P.unit;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int gend = tplan ? tplan[2 + u] : min(P.G, (u + 1) * P.unit);
+            int g0 = tplan ? tplan[1 + u] : u * P.unit;
             while (g0 < gend) {
                 int g1 = fm_tile_end(P.node_ptr, g0, gend, lane);
                 if (g1 == g0) { g0 += 1; continue; }
@@ -380,9 +387,9 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
             ++n_aready;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         };
-        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
-            const int gend = min(P.G, (u + 1) * P.unit);
-            int g0 = u * P.unit;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int gend = tplan ? tplan[2 + u] : min(P.G, (u + 1) * P.unit);
+            int g0 = tplan ? tplan[1 + u] : u * P.unit;
             while (g0 < gend) {
                 int g1 = fm_tile_end(P.node_ptr, g0, gend, lane);
                 if (g1 == g0) { g0 += 1; continue; }
@@ -542,9 +549,9 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
 
         bool first_tile = true;
         (void)first_tile;
-        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
-            const int gend = min(P.G, (u + 1) * P.unit);
-            int g0 = u * P.unit;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int gend = tplan ? tplan[2 + u] : min(P.G, (u + 1) * P.unit);
+            int g0 = tplan ? tplan[1 + u] : u * P.unit;
             while (g0 < gend) {
                 const int g1 = fm_tile_end(P.node_ptr, g0, gend, lane);
                 if (g1 == g0) {
@@ -866,11 +873,41 @@ template <int D>
 static int fm_launch(const CUtensorMap &hi, const CUtensorMap &lo, const FmParams &p, cudaStream_t stream) {
     constexpr int smem = FmCfg<D>::SMEM;
     GSN_CUDA_OK(cudaFuncSetAttribute(fused_model_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const unsigned grid = (unsigned)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
+    const unsigned grid = (unsigned)(p.n_units < kNumSMs ? p.n_units : kNumSMs);      // with a tile plan: n_units = its capacity
     fused_model_kernel<D><<<grid, FM_THREADS, smem, stream>>>(hi, lo, p);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("fused_model_kernel");
     return GSN_OK;
+}
+
+// Greedy tile plan of a small batch (see gsn_tile_plan in the header): node_ptr staged in shared memory, one warp walks it
+// with the same 32-graph probe the model kernel uses inside a unit (fm_tile_end).
+__global__ void tile_plan_kernel(const int64_t *__restrict__ node_ptr, int G, int32_t *__restrict__ plan, int cap,
+                                 int32_t *status) {
+    extern __shared__ int32_t tp_ptr[];
+    for (int i = threadIdx.x; i <= G; i += blockDim.x) tp_ptr[i] = (int32_t)node_ptr[i];
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    int g0 = 0, t = 0;
+    while (g0 < G) {
+        const int g = g0 + 1 + lane;
+        const bool ok = g <= G && tp_ptr[g] - tp_ptr[g0] <= FM_ROWS;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        int cnt = (m == 0xffffffffu) ? 32 : (__ffs((int)~m) - 1);
+        if (cnt == 0) cnt = 1;                      // wider than a tile: alone, the model kernel reports it
+        if (lane == 0 && t < cap) plan[1 + t] = g0;
+        ++t;
+        g0 += cnt;
+    }
+    if (lane == 0) {
+        if (t > cap) {                               // cannot happen with the documented capacity
+            atomicOr(status, GSN_S_GRAPH_TOO_LARGE);
+            t = cap;
+        }
+        plan[0] = t;
+        plan[1 + t] = G;
+    }
 }
 
 }  // namespace gsn
@@ -897,6 +934,11 @@ extern "C" int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream_) {
     p.rowptr = m.d_rowptr; p.nbr = m.d_nbr; p.node_ptr = m.d_node_ptr;
     p.x0 = m.d_x0; p.x0_ld = m.x0_ld; p.x0_d = m.x0_d;
     p.G = (int32_t)m.G; p.unit = m.graphs_per_unit; p.n_units = (int32_t)ceil_div(m.G, m.graphs_per_unit);
+    p.tile_plan = m.d_tile_plan;
+    if (m.d_tile_plan) {
+        if (m.max_tiles < 1) return GSN_E_INVALID;
+        p.n_units = m.max_tiles;          // the grid: CTAs past the plan's tile count exit
+    }
     p.status = m.d_status;
     for (int l = 0; l < m.n_layers; ++l) {
         const GsnFusedLayer &s = m.layers[l];
@@ -921,4 +963,15 @@ extern "C" int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (m.D == 128) return fm_launch<128>(hi, lo, p, stream);
     return fm_launch<64>(hi, lo, p, stream);
+}
+
+extern "C" int gsn_tile_plan(const int64_t *d_node_ptr, int64_t G, int32_t *d_tile_plan, int32_t max_tiles, int32_t *d_status,
+                             void *stream_) {
+    if (!d_node_ptr || !d_tile_plan || !d_status || G < 0 || max_tiles < 1) return GSN_E_INVALID;
+    if (G > 8192) return GSN_E_UNSUPPORTED;
+    tile_plan_kernel<<<1, 256, sizeof(int32_t) * (size_t)(G + 1), (cudaStream_t)stream_>>>(d_node_ptr, (int)G, d_tile_plan,
+                                                                                          max_tiles, d_status);
+    GSN_BUMP(1);
+    GSN_LAUNCH_OK("tile_plan_kernel");
+    return GSN_OK;
 }

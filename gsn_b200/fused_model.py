@@ -26,6 +26,7 @@ from .fused import FusedForward, supported as _fused_supported
 MAX_LAYERS = 8
 MAX_TILE_ROWS = 128
 _ACT = ops.ACTIVATIONS
+FILL_ROWS = 100.0      # rows' worth of graphs per unit of work for small batches (see FusedModel.__call__)
 (V_CJ, V_CI, V_SHIFT, V_CU, V_CF, V_CV, V_CB, V_C2S, V_C2B) = range(9)
 
 
@@ -43,7 +44,8 @@ class GsnFusedModel(ctypes.Structure):
                 ('n_mats', ctypes.c_int32), ('graphs_per_unit', ctypes.c_int32), ('Whi', ctypes.c_void_p),
                 ('Wlo', ctypes.c_void_p), ('rowptr', ctypes.c_void_p), ('nbr', ctypes.c_void_p),
                 ('node_ptr', ctypes.c_void_p), ('x0', ctypes.c_void_p), ('x0_ld', ctypes.c_int32), ('x0_d', ctypes.c_int32),
-                ('N', ctypes.c_int64), ('E', ctypes.c_int64), ('G', ctypes.c_int64), ('status', ctypes.c_void_p)]
+                ('N', ctypes.c_int64), ('E', ctypes.c_int64), ('G', ctypes.c_int64), ('status', ctypes.c_void_p),
+                ('tile_plan', ctypes.c_void_p), ('max_tiles', ctypes.c_int32), ('_pad', ctypes.c_int32)]
 
 
 def split_fp16_rows(W: torch.Tensor):
@@ -175,7 +177,10 @@ class FusedModel(FusedForward):
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def __call__(self, data, raw_identifiers: Optional[torch.Tensor] = None, vocab: Optional[List[torch.Tensor]] = None):
+    def __call__(self, data, raw_identifiers: Optional[torch.Tensor] = None, vocab: Optional[List[torch.Tensor]] = None,
+                 tile_plan: Optional[torch.Tensor] = None):
+        """tile_plan: optional result of `tile_plan()` for this batch's node_ptr (small batches: one CTA per greedily
+        packed tile); without it a CTA takes `graphs_per_unit` consecutive graphs"""
         m = self.model
         ctx = self._context(data, raw_identifiers, vocab)       # (re)prepares when the weights changed
         dev, N, E = ctx['dev'], ctx['N'], ctx['E']
@@ -223,8 +228,11 @@ class FusedModel(FusedForward):
             # filled: ~100 rows' worth of graphs per unit (one tile, rarely two) for small batches -- a step then occupies
             # few SMs and steps of other streams run beside it -- and >= 2 units per SM for large ones
             avg = max(1.0, N / max(G, 1))
-            gpu = max(1, int(100.0 / avg), -(-G // (2 * 148)))
+            gpu = max(1, int(FILL_ROWS / avg), -(-G // (2 * 148)))
         fm.graphs_per_unit = int(gpu)
+        if tile_plan is not None:
+            fm.tile_plan, fm.max_tiles = tile_plan.data_ptr(), int(tile_plan.numel() - 2)
+            keep.append(tile_plan)
         fm.Whi, fm.Wlo = self.Whi.data_ptr(), self.Wlo.data_ptr()
         fm.rowptr, fm.nbr, fm.node_ptr = plan.rowptr.data_ptr(), plan.nbr.data_ptr(), node_ptr.data_ptr()
         x0 = ctx['x']
@@ -243,3 +251,21 @@ class FusedModel(FusedForward):
         bits = (int(self.status.item()) if getattr(self, 'status', None) is not None else 0) & _lib.S_FATAL
         if bits:
             raise RuntimeError('fused model kernel: ' + _lib.status_message(bits))
+
+
+TILE_PLAN_MAX_GRAPHS = 4096      # beyond this a CTA takes a run of graphs_per_unit graphs and cuts it into tiles itself
+
+
+def tile_plan(node_ptr: torch.Tensor, N: int, status: torch.Tensor) -> Optional[torch.Tensor]:
+    """Greedy packing of the batch's graphs into tiles of <= 128 rows (`gsn_tile_plan`): int32 [max_tiles + 2] on the
+    device, or None for batches too large for the one-CTA scan (they do not need it: with hundreds of graphs per CTA only
+    the last tile of a run is underfilled)."""
+    G = int(node_ptr.numel() - 1)
+    if G < 1 or G > TILE_PLAN_MAX_GRAPHS:
+        return None
+    cap = min(G, 2 * int(N) // 128 + G // 32 + 2)
+    plan = torch.empty(cap + 2, dtype=torch.int32, device=node_ptr.device)
+    with torch.cuda.device(node_ptr.device):
+        _lib.call('tile_plan', 'gsn_tile_plan', node_ptr.data_ptr(), G, plan.data_ptr(), cap, status.data_ptr(),
+                  _lib.stream_ptr())
+    return plan

@@ -74,10 +74,11 @@ class GSNPipeline:
         self._out: Optional[torch.Tensor] = None
         self.last_status: Optional[torch.Tensor] = None
         self._side: Optional[torch.cuda.Stream] = None
+        self.use_tile_plan = True       # small batches: greedy packing of graphs into the forward's tiles (gsn_tile_plan)
 
     # -- one eager step on device-resident inputs --------------------------------
     def step(self, t: Dict[str, torch.Tensor]) -> torch.Tensor:
-        from . import encoders, ops
+        from . import encoders, fused_model as _fm, ops
         ops.clear_plan_cache()            # a step is a new batch: never reuse groupings across steps
         encoders._pool_plans.clear()
         N, G = int(t['x'].shape[0]), int(t['node_ptr'].numel() - 1)
@@ -92,6 +93,9 @@ class GSNPipeline:
         with torch.cuda.stream(self._side):
             flow = self.model.conv[0].flow
             ops.edge_plan(t['edge_index'], N, flow, status=status).degree()
+            tiles = None
+            if self.use_tile_plan and isinstance(self.fused, _fm.FusedModel):
+                tiles = _fm.tile_plan(t['node_ptr'], N, status)        # which graphs share a tile (small batches)
         ids = counting.count_batch(t['edge_index'], t['node_ptr'], self.subgraph_dicts, self.induced, self.id_scope,
                                    num_nodes=N, max_nodes_per_graph=self.max_nodes, check=False, status=status)
         self.last_status = status
@@ -99,6 +103,8 @@ class GSNPipeline:
         if self.fused is not None:
             data = Batch(x=t['x'], edge_index=t['edge_index'], edge_features=t['edge_features'], batch=t['batch'],
                          degrees=t['degrees'], node_ptr=t['node_ptr'], num_graphs=G)
+            if tiles is not None:
+                return self.fused(data, raw_identifiers=ids, vocab=self.encoder.vocab, tile_plan=tiles)
             return self.fused(data, raw_identifiers=ids, vocab=self.encoder.vocab)
         data = Batch(x=t['x'], edge_index=t['edge_index'], edge_features=t['edge_features'], batch=t['batch'],
                      degrees=t['degrees'], identifiers=self.encoder(ids), num_graphs=G)

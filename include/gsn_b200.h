@@ -401,8 +401,20 @@ typedef struct GsnFusedModel {
     const float *d_x0; int32_t x0_ld, x0_d;
     int64_t N, E, G;
     int32_t *d_status;
+    const int32_t *d_tile_plan;   /* optional (gsn_tile_plan): one CTA per tile instead of graphs_per_unit graphs per CTA */
+    int32_t max_tiles;            /* capacity the plan was built with */
+    int32_t _pad;
 } GsnFusedModel;
 int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream);
+/*
+ * Tiles of the one-kernel forward for a small batch: consecutive whole graphs packed greedily into tiles of <= 128 rows and
+ * <= 32 graphs (the collation of main.py:243-258 decides which graphs share a batch; this decides which share an SM).
+ * d_tile_plan: int32 [max_tiles + 2] = { n_tiles, first graph of tile 0, ..., first graph of tile n_tiles - 1, G }.
+ * A graph with more than 128 rows becomes a tile of its own (gsn_fused_model_fwd then reports GSN_S_GRAPH_TOO_LARGE).
+ * max_tiles >= min(G, 2 * N / 128 + G / 32 + 2) always suffices; G <= 8192 (one CTA scans node_ptr from shared memory).
+ */
+int gsn_tile_plan(const int64_t *d_node_ptr, int64_t G, int32_t *d_tile_plan, int32_t max_tiles, int32_t *d_status,
+                  void *stream);
 
 /* ------------------------------------------------------------------ */
 /* DGN consumer of COUNT (directional_gsn/)                            */

@@ -90,6 +90,7 @@ def test_one_kernel_pipeline_vs_per_layer_fused_path(B, unit, d_out, id_scope):
         p_one = GSNPipeline(model, sds, False, id_scope, enc, 64, fused='model')
         assert isinstance(p_one.fused, fused_model.FusedModel) and not isinstance(p_ref.fused, fused_model.FusedModel)
         p_one.fused.graphs_per_unit = unit
+        p_one.use_tile_plan = unit is None          # a forced unit exercises the in-kernel cutting of runs into tiles
         p_one.fused.debug_x_out = True
         out_ref = p_ref.step(t)
         out_one = p_one.step(t)
@@ -143,6 +144,36 @@ def test_one_kernel_wide_dynamic_range_rows():
         assert float(((xo[:, :xr.shape[1]] - xr).abs() / rows).max()) < 2 * TOL
     scale = max(float(ref_out.abs().max()), 1.0)
     torch.testing.assert_close(out, ref_out, atol=2 * TOL * scale, rtol=2 * TOL)
+
+
+def test_tile_plan_greedy_packing():
+    """gsn_tile_plan: whole graphs, <= 128 rows and <= 32 graphs per tile, greedy; oversized graphs alone; the forward
+    with the plan equals the forward without it bit for bit (a row's result does not depend on its tile mates)"""
+    from gsn_b200 import fused_model
+    from gsn_b200.pipeline import GSNPipeline
+    g = torch.Generator().manual_seed(3)
+    for sizes in (torch.randint(9, 38, (128,), generator=g), torch.randint(0, 4, (300,), generator=g),
+                  torch.tensor([128, 1, 127, 129, 5, 200, 64, 64, 1]), torch.tensor([7])):
+        ptr = torch.cat([torch.zeros(1, dtype=torch.int64), sizes.cumsum(0)])
+        status = torch.zeros(1, dtype=torch.int32, device='cuda')
+        plan = fused_model.tile_plan(ptr.cuda(), int(ptr[-1]), status).cpu()
+        exp, g0, G = [], 0, len(sizes)
+        while g0 < G:
+            g1 = g0
+            while g1 < G and g1 - g0 < 32 and int(ptr[g1 + 1] - ptr[g0]) <= 128:
+                g1 += 1
+            g1 = max(g1, g0 + 1)
+            exp.append(g0)
+            g0 = g1
+        assert int(plan[0]) == len(exp) <= plan.numel() - 2 and int(status.item()) == 0
+        assert plan[1:1 + len(exp)].tolist() == exp and int(plan[1 + len(exp)]) == G
+    model, sds, enc, b, t, _ = _zinc_setup(128, 3)
+    with torch.no_grad():
+        p = GSNPipeline(model, sds, False, 'local', enc, 64, fused='model')
+        out_plan = p.step(t).clone()
+        p.use_tile_plan = False
+        out_unit = p.step(t).clone()
+    assert torch.equal(out_plan, out_unit)
 
 
 def test_one_kernel_rejects_oversized_graphs():
