@@ -205,7 +205,7 @@ class FusedForward:
         self._stamp = self._version_stamp()
 
     # ------------------------------------------------------------------ categorical inputs -> table rows
-    def _context(self, data, raw_identifiers, vocab):
+    def _context(self, data, raw_identifiers, vocab, need_ids=True):
         """per-call state shared by the layers: dense x (or None), index columns, the concatenated vocabulary"""
         m = self.model
         if m.training:
@@ -213,7 +213,7 @@ class FusedForward:
         if self._stamp != self._version_stamp():
             self.prepare()
         # identifier rows into the one-hot table of the id encoder (offset inside the table added later)
-        ids = raw_identifiers if raw_identifiers is not None else data.identifiers
+        ids = (raw_identifiers if raw_identifiers is not None else data.identifiers) if need_ids else None
         id_dims = m.id_encoder[0].encoder.d_in
         id_off, o = [], 0
         for d in id_dims:
@@ -235,7 +235,7 @@ class FusedForward:
             vcat, vptr = None, [None] * len(id_dims)
         x_cat = _is_onehot(m.input_node_encoder)
         xi = data.x if data.x.dim() == 2 else data.x.unsqueeze(-1)
-        x = None if x_cat else m.input_node_encoder(data.x)
+        x = None if (x_cat or not need_ids) else m.input_node_encoder(data.x)
         efi = None
         if getattr(data, 'edge_features', None) is not None:
             efi = data.edge_features if data.edge_features.dim() == 2 else data.edge_features.unsqueeze(-1)
@@ -243,36 +243,65 @@ class FusedForward:
         if getattr(self, 'status', None) is None or self.status.device != dev0:
             self.status = torch.zeros(1, dtype=torch.int32, device=dev0)
         return {'ids': ids, 'id_off': id_off, 'vcat': vcat, 'vptr': vptr, 'xi': xi, 'x': x, 'efi': efi, 'status': self.status,
-                'N': data.x.shape[0], 'E': data.edge_index.shape[1], 'dev': data.edge_index.device, 'ef_rows_cache': {}}
+                'N': data.x.shape[0], 'E': data.edge_index.shape[1], 'dev': data.edge_index.device, 'ef_rows_cache': {},
+                'pre': self._take_prefetched(data) if need_ids else {}}
 
-    def _layer_rows(self, L, ctx, plan):
-        """(node_rows int32 [N, n_node_cols] | None, edge_rows int32 [E, n_groups] in CSR order | None) of one layer"""
-        ids, vptr, id_off, vcat, dev = ctx['ids'], ctx['vptr'], ctx['id_off'], ctx['vcat'], ctx['dev']
-        node_cols, edge_cols = [], []
+    # index rows that do not depend on the identifiers can be produced before COUNT has finished
+    def prefetch_rows(self, data):
+        """Call on a side stream while COUNT runs: encodes the rows of the categorical inputs that do not involve the
+        identifiers (atom types; bond types of layers without edge identifiers).  The next __call__ on the same tensors
+        picks them up; the caller joins the streams in between."""
+        ctx = self._context(data, None, None, need_ids=False)
+        rows = {}
+        for li, L in enumerate(self.layers):
+            ids_nodes, ids_edges = L['uses_ids'] and not L['local'], L['uses_ids'] and L['local']
+            if L['x_cat'] and not ids_nodes:
+                rows[('n', li)] = self._node_rows(L, ctx)
+            if L['uses_ef'] and L['ef_cat'] and not ids_edges:
+                plan = ops.edge_plan(data.edge_index, ctx['N'], L['flow'])
+                rows[('e', L['Te_off_ef'], L['flow'])] = self._edge_rows(L, ctx, plan)
+        self._prefetched = ((data.x.data_ptr(), data.edge_index.data_ptr()), rows)
+
+    def _take_prefetched(self, data):
+        pre = getattr(self, '_prefetched', None)
+        self._prefetched = None
+        if pre is not None and pre[0] == (data.x.data_ptr(), data.edge_index.data_ptr()):
+            return pre[1]
+        return {}
+
+    def _node_rows(self, L, ctx):
+        ids, vptr, id_off, vcat = ctx['ids'], ctx['vptr'], ctx['id_off'], ctx['vcat']
         m = self.model
+        node_cols = []
         if L['x_cat']:
             node_cols.append((ctx['xi'][:, 0], None, 0, int(m.input_node_encoder.encoder.d_in[0])))
-        if L['uses_ids']:
+        if L['uses_ids'] and not L['local']:
             id_dims = m.id_encoder[0].encoder.d_in
-            cols = [(ids[:, c], vptr[c], id_off[c], 0 if vptr[c] is not None else int(id_dims[c])) for c in range(ids.shape[1])]
-            if L['local']:
-                edge_cols += cols
-            else:
-                node_cols += [(s, v, off + L['Tn_off_ids'], r) for s, v, off, r in cols]
+            node_cols += [(ids[:, c], vptr[c], id_off[c] + L['Tn_off_ids'], 0 if vptr[c] is not None else int(id_dims[c]))
+                          for c in range(ids.shape[1])]
+        return ops.encode_rows(node_cols, vcat, ctx['N'], ctx['dev'], status=ctx['status']) if node_cols else None
+
+    def _edge_rows(self, L, ctx, plan):
+        ids, vptr, id_off, vcat, dev = ctx['ids'], ctx['vptr'], ctx['id_off'], ctx['vcat'], ctx['dev']
+        m = self.model
+        edge_cols = []
+        if L['uses_ids'] and L['local']:
+            id_dims = m.id_encoder[0].encoder.d_in
+            edge_cols += [(ids[:, c], vptr[c], id_off[c], 0 if vptr[c] is not None else int(id_dims[c]))
+                          for c in range(ids.shape[1])]
         if L['uses_ef'] and L['ef_cat']:
             edge_cols.append((ctx['efi'][:, 0], None, L['Te_off_ef'], int(L['ef_rows'])))
         eg = L['edge_groups']
         if eg is not None:
             edge_cols = [(s, v, eg['off'][c], r) for c, (s, v, _, r) in enumerate(edge_cols)]
         st = ctx['status']
-        node_rows = ops.encode_rows(node_cols, vcat, ctx['N'], dev, status=st) if node_cols else None
         # edge rows are produced directly in CSR order (perm = plan.eid): the message kernel then reads them
         # sequentially instead of chasing eid -> row
         only_ef = len(edge_cols) == 1 and L['uses_ef'] and L['ef_cat']
         key = (L['Te_off_ef'], L['flow'])
         cache = ctx['ef_rows_cache']
         if only_ef and key in cache:
-            return node_rows, cache[key]
+            return cache[key]
         if eg is not None:
             edge_rows = ops.encode_rows_grouped(edge_cols, eg['group'], eg['mult'], eg['n_groups'], vcat, ctx['E'], dev,
                                                 perm=plan.eid, status=st)
@@ -280,6 +309,16 @@ class FusedForward:
             edge_rows = ops.encode_rows(edge_cols, vcat, ctx['E'], dev, perm=plan.eid, status=st) if edge_cols else None
         if only_ef:
             cache[key] = edge_rows
+        return edge_rows
+
+    def _layer_rows(self, L, ctx, plan):
+        """(node_rows int32 [N, n_node_cols] | None, edge_rows int32 [E, n_groups] in CSR order | None) of one layer"""
+        pre = ctx['pre']
+        li = next(i for i, l_ in enumerate(self.layers) if l_ is L)
+        node_rows = pre[('n', li)] if ('n', li) in pre else self._node_rows(L, ctx)
+        ekey = ('e', L['Te_off_ef'], L['flow'])
+        ids_edges = L['uses_ids'] and L['local']
+        edge_rows = pre[ekey] if (ekey in pre and not ids_edges) else self._edge_rows(L, ctx, plan)
         return node_rows, edge_rows
 
     # ------------------------------------------------------------------ forward

@@ -90,19 +90,25 @@ class GSNPipeline:
         if self._side is None:
             self._side = torch.cuda.Stream()
         self._side.wait_stream(cur)
+        one_kernel = isinstance(self.fused, _fm.FusedModel)
+        data = Batch(x=t['x'], edge_index=t['edge_index'], edge_features=t['edge_features'], batch=t['batch'],
+                     degrees=t['degrees'], node_ptr=t['node_ptr'], num_graphs=G)
         with torch.cuda.stream(self._side):
             flow = self.model.conv[0].flow
-            ops.edge_plan(t['edge_index'], N, flow, status=status).degree()
+            plan = ops.edge_plan(t['edge_index'], N, flow, status=status)
             tiles = None
-            if self.use_tile_plan and isinstance(self.fused, _fm.FusedModel):
-                tiles = _fm.tile_plan(t['node_ptr'], N, status)        # which graphs share a tile (small batches)
+            if one_kernel:
+                if self.use_tile_plan:
+                    tiles = _fm.tile_plan(t['node_ptr'], N, status)    # which graphs share a tile (small batches)
+            else:
+                plan.degree()
+            if self.fused is not None:
+                self.fused.prefetch_rows(data)        # index rows of the inputs that do not involve the identifiers
         ids = counting.count_batch(t['edge_index'], t['node_ptr'], self.subgraph_dicts, self.induced, self.id_scope,
                                    num_nodes=N, max_nodes_per_graph=self.max_nodes, check=False, status=status)
         self.last_status = status
         cur.wait_stream(self._side)
         if self.fused is not None:
-            data = Batch(x=t['x'], edge_index=t['edge_index'], edge_features=t['edge_features'], batch=t['batch'],
-                         degrees=t['degrees'], node_ptr=t['node_ptr'], num_graphs=G)
             if tiles is not None:
                 return self.fused(data, raw_identifiers=ids, vocab=self.encoder.vocab, tile_plan=tiles)
             return self.fused(data, raw_identifiers=ids, vocab=self.encoder.vocab)
