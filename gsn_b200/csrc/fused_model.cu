@@ -46,6 +46,8 @@ struct FmLayer {
     const int32_t *edge_rows; const float *Te;
     const float *vec; float *pooled; float *x_out;
     int32_t n_node_cols, tu_stride, n_edge_cols, te_rows, has_dense, mat0, act_msg, act_upd, act_out, pool;
+    const float *jk_W0T, *jk_vec, *jk_W1, *jk_b1;
+    int32_t jk_kind, jk_act, jk_first;       // jk_first: the first projecting layer writes `out`, later ones add
 };
 
 struct FmParams {
@@ -57,6 +59,8 @@ struct FmParams {
     int32_t x0_ld, x0_d;
     int32_t G, unit, n_units;
     const int32_t *tile_plan;     // optional: { n_tiles, first graph of every tile, G }
+    float *out;                   // [G, n_out] in-kernel JK head
+    int32_t n_out;
     int32_t *status;
 };
 
@@ -807,16 +811,83 @@ fused_model_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
                             // rows of a graph summed in row order -> deterministic
                             fm_bar_compute();
                             const int col = ct % D;
-                            for (int g = g0 + ct / D; g < g1; g += FM_COMPUTE_THREADS / D) {
-                                const int ra = (int)(__ldg(P.node_ptr + g) - row0), rb = (int)(__ldg(P.node_ptr + g + 1) - row0);
-                                float acc = 0.f;
-                                for (int rr = ra; rr < rb; ++rr) {
-                                    float t;
-                                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sPJ + fm_swz<D>((rr & 3) * 32 + (rr >> 2), col >> 2) + (uint32_t)((col & 3) << 2)));
-                                    acc += t;
+                            constexpr int GPP = FM_COMPUTE_THREADS / D;       // graphs per pass of the pooling loop
+                            constexpr int MAXP = 32 / GPP;                    // a tile holds <= 32 graphs
+                            float pv[MAXP];
+#pragma unroll
+                            for (int k = 0; k < MAXP; ++k) pv[k] = 0.f;
+#pragma unroll
+                            for (int k = 0; k < MAXP; ++k) {
+                                const int g = g0 + ct / D + k * GPP;
+                                if (g < g1) {
+                                    const int ra = (int)(__ldg(P.node_ptr + g) - row0), rb = (int)(__ldg(P.node_ptr + g + 1) - row0);
+                                    float acc = 0.f;
+                                    for (int rr = ra; rr < rb; ++rr) {
+                                        float t;
+                                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sPJ + fm_swz<D>((rr & 3) * 32 + (rr >> 2), col >> 2) + (uint32_t)((col & 3) << 2)));
+                                        acc += t;
+                                    }
+                                    if (L.pool == 2 && rb > ra) acc /= (float)(rb - ra);
+                                    if (L.pooled) L.pooled[(int64_t)g * D + col] = acc;
+                                    pv[k] = acc;
                                 }
-                                if (L.pool == 2 && rb > ra) acc /= (float)(rb - ra);
-                                L.pooled[(int64_t)g * D + col] = acc;
+                            }
+                            if (L.jk_kind) {
+                                // ---- JK head of this readout (models_graph_classification.py:236-240): the pooled rows and
+                                //      the hidden rows of the head live in the (now consumed) P_j buffer, plain [graph][col]
+                                float *sPool = reinterpret_cast<float *>(sm + C::OFF_PJ);
+                                float *sHid = sPool + 32 * D;
+                                const int ng = g1 - g0;
+                                fm_bar_compute();                      // every pooling read of the buffer is done
+#pragma unroll
+                                for (int k = 0; k < MAXP; ++k)
+                                    if (ct / D + k * GPP < ng) sPool[(ct / D + k * GPP) * D + col] = pv[k];
+                                fm_bar_compute();
+                                const float *sIn = sPool;
+                                if (L.jk_kind == 2) {
+                                    // hidden rows: the k range is split over the GPP thread groups (every weight is read once
+                                    // per tile, all loads of a thread in flight together), partial sums meet in shared memory
+                                    constexpr int KPT = D / GPP;              // k values per thread
+                                    float *sPart = sHid + 32 * D;             // [GPP][8][D]
+                                    const int kq = ct / D;
+                                    const float b0 = __ldg(L.jk_vec + col), s0 = __ldg(L.jk_vec + D + col), t0 = __ldg(L.jk_vec + 2 * D + col);
+                                    for (int gb = 0; gb < ng; gb += 8) {
+                                        float a[8];
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll 16
+                                        for (int kk = 0; kk < KPT; ++kk) {
+                                            const int k = kq * KPT + kk;
+                                            const float w = __ldg(L.jk_W0T + k * D + col);
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) a[j] = fmaf(sPool[(gb + j) * D + k], w, a[j]);
+                                        }
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) sPart[(kq * 8 + j) * D + col] = a[j];
+                                        fm_bar_compute();
+                                        for (int j = kq; j < 8 && gb + j < ng; j += GPP) {
+                                            float h = 0.f;
+#pragma unroll
+                                            for (int qq = 0; qq < GPP; ++qq) h += sPart[(qq * 8 + j) * D + col];
+                                            sHid[(gb + j) * D + col] = fm_act(fmaf(h + b0, s0, t0), L.jk_act);
+                                        }
+                                        fm_bar_compute();
+                                    }
+                                    sIn = sHid;
+                                }
+                                // out[g, c] (+)= <row, W1[c, :]> + b1[c]: one warp per (graph, output column)
+                                for (int pr = cw; pr < ng * P.n_out; pr += FM_COMPUTE_THREADS / 32) {
+                                    const int gi = pr / P.n_out, c = pr % P.n_out;
+                                    float a = 0.f;
+                                    for (int k = lane; k < D; k += 32) a = fmaf(sIn[gi * D + k], __ldg(L.jk_W1 + c * D + k), a);
+#pragma unroll
+                                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                                    if (lane == 0) {
+                                        float *dst = P.out + (int64_t)(g0 + gi) * P.n_out + c;
+                                        a += __ldg(L.jk_b1 + c);
+                                        *dst = L.jk_first ? a : *dst + a;
+                                    }
+                                }
                             }
                         }
                         if (l + 1 < nL) rx_inv = finish_operand(m, live);
@@ -940,12 +1011,13 @@ extern "C" int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream_) {
         p.n_units = m.max_tiles;          // the grid: CTAs past the plan's tile count exit
     }
     p.status = m.d_status;
+    bool any_jk = false;
     for (int l = 0; l < m.n_layers; ++l) {
         const GsnFusedLayer &s = m.layers[l];
         FmLayer &d = p.layer[l];
         if (!s.d_vec || s.n_node_cols < 0 || s.n_edge_cols < 0 || (s.n_node_cols > 0 && (!s.d_node_rows || !s.d_Tn)) ||
             (s.n_edge_cols > 0 && (!s.d_edge_rows || !s.d_Te || s.te_rows < 1)) || (s.d_Tu && !s.d_tu_rows) ||
-            (s.pool && !s.d_pooled) || s.mat0 < 0 || s.mat0 + (s.has_dense ? 5 : 2) > m.n_mats)
+            s.mat0 < 0 || s.mat0 + (s.has_dense ? 5 : 2) > m.n_mats)
             return GSN_E_INVALID;
         if (s.has_dense && l == 0 && (!m.d_x0 || m.x0_d < 1 || m.x0_d > m.D)) return GSN_E_INVALID;
         if (!s.has_dense && l > 0) return GSN_E_UNSUPPORTED;      // a layer after the first always consumes dense rows
@@ -955,7 +1027,19 @@ extern "C" int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream_) {
         d.n_node_cols = s.n_node_cols; d.tu_stride = s.tu_stride; d.n_edge_cols = s.n_edge_cols; d.te_rows = s.te_rows;
         d.has_dense = s.has_dense ? 1 : 0; d.mat0 = s.mat0; d.act_msg = s.act_msg; d.act_upd = s.act_upd; d.act_out = s.act_out;
         d.pool = s.pool;
+        d.jk_kind = s.jk_kind; d.jk_act = s.jk_act; d.jk_W0T = s.d_jk_W0T; d.jk_vec = s.d_jk_vec; d.jk_W1 = s.d_jk_W1;
+        d.jk_b1 = s.d_jk_b1;
+        d.jk_first = 0;
+        if (s.jk_kind) {
+            if (s.jk_kind < 0 || s.jk_kind > 2 || !s.pool || !s.d_jk_W1 || !s.d_jk_b1 || !m.d_out || m.n_out < 1 || m.n_out > 32 ||
+                (s.jk_kind == 2 && (!s.d_jk_W0T || !s.d_jk_vec)))
+                return GSN_E_INVALID;
+            d.jk_first = any_jk ? 0 : 1;
+            any_jk = true;
+        }
+        if (s.pool && !s.d_pooled && !s.jk_kind) return GSN_E_INVALID;
     }
+    p.out = m.d_out; p.n_out = m.n_out;
     CUtensorMap hi, lo;
     int rc;
     if ((rc = fm_make_map(&hi, m.d_Whi, (int64_t)m.n_mats * m.D, m.D))) return rc;

@@ -26,6 +26,7 @@ from .fused import FusedForward, supported as _fused_supported
 MAX_LAYERS = 8
 MAX_TILE_ROWS = 128
 _ACT = ops.ACTIVATIONS
+JK_IN_KERNEL = True     # evaluate the JK head inside the model kernel when its shape allows (False: two more GEMM launches)
 FILL_ROWS = 100.0      # rows' worth of graphs per unit of work for small batches (see FusedModel.__call__)
 (V_CJ, V_CI, V_SHIFT, V_CU, V_CF, V_CV, V_CB, V_C2S, V_C2B) = range(9)
 
@@ -35,7 +36,9 @@ class GsnFusedLayer(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('node_rows', 'Tn', 'tu_rows', 'Tu', 'edge_rows', 'Te', 'vec', 'pooled',
                                                'x_out')] + \
                [(n, ctypes.c_int32) for n in ('n_node_cols', 'tu_stride', 'n_edge_cols', 'te_rows', 'has_dense', 'mat0',
-                                              'act_msg', 'act_upd', 'act_out', 'pool')]
+                                              'act_msg', 'act_upd', 'act_out', 'pool')] + \
+               [(n, ctypes.c_void_p) for n in ('jk_W0T', 'jk_vec', 'jk_W1', 'jk_b1')] + \
+               [('jk_kind', ctypes.c_int32), ('jk_act', ctypes.c_int32)]
 
 
 class GsnFusedModel(ctypes.Structure):
@@ -45,7 +48,8 @@ class GsnFusedModel(ctypes.Structure):
                 ('Wlo', ctypes.c_void_p), ('rowptr', ctypes.c_void_p), ('nbr', ctypes.c_void_p),
                 ('node_ptr', ctypes.c_void_p), ('x0', ctypes.c_void_p), ('x0_ld', ctypes.c_int32), ('x0_d', ctypes.c_int32),
                 ('N', ctypes.c_int64), ('E', ctypes.c_int64), ('G', ctypes.c_int64), ('status', ctypes.c_void_p),
-                ('tile_plan', ctypes.c_void_p), ('max_tiles', ctypes.c_int32), ('_pad', ctypes.c_int32)]
+                ('tile_plan', ctypes.c_void_p), ('max_tiles', ctypes.c_int32), ('n_out', ctypes.c_int32),
+                ('out', ctypes.c_void_p)]
 
 
 def split_fp16_rows(W: torch.Tensor):
@@ -170,6 +174,32 @@ class FusedModel(FusedForward):
             F['act_msg'] = F['act_upd'] = _ACT[L['act_mlp']]
             F['act_out'] = _ACT[self._act_model]
             self.fm_layers.append(F)
+        # JK head in the kernel (models_graph_classification.py:236-240) when every projection reads a layer output of
+        # width <= D and the head is narrow; otherwise the kernel writes the pooled rows and the caller projects them
+        self.jk = None
+        prs = [pr for pr in self.proj if pr is not None]
+        if prs and self.proj[0] is None and JK_IN_KERNEL:
+            n_out = prs[0][5].shape[0] if prs[0][0] == 'mlp' else prs[0][1].shape[0]
+            ok = n_out <= 32
+            jk = [None]
+            for pr in self.proj[1:]:
+                if pr is None:
+                    jk.append(None)
+                    continue
+                if pr[0] == 'linear':
+                    _, W1, b1 = pr
+                    ok = ok and W1.shape[1] <= D and W1.shape[0] == n_out
+                    jk.append({'kind': 1, 'act': 0, 'W0T': None, 'vec': None, 'W1': pad_cols(W1, D).contiguous(),
+                               'b1': b1.float().contiguous()} if ok else None)
+                else:
+                    _, W0, b0, sc, sh, W1, b1, act = pr
+                    ok = ok and max(W0.shape) <= D and W1.shape[1] <= D and W1.shape[0] == n_out
+                    if ok:
+                        vec = torch.stack([pad_vec(b0), pad_vec(sc, 1.0), pad_vec(sh)])
+                        jk.append({'kind': 2, 'act': _ACT[act], 'W0T': pad_mat(W0).t().contiguous(), 'vec': vec.contiguous(),
+                                   'W1': pad_cols(W1, D).contiguous(), 'b1': b1.float().contiguous()})
+            if ok:
+                self.jk, self.n_out = jk, int(n_out)
         self.n_mats = len(mats)
         self.Whi = torch.cat([h for h, _ in mats], 0).contiguous()
         self.Wlo = torch.cat([l for _, l in mats], 0).contiguous()
@@ -210,7 +240,14 @@ class FusedModel(FusedForward):
                 fl.Te, fl.te_rows = F['Te'].data_ptr(), F['Te'].shape[0]
             if F['Tu'] is not None:
                 fl.Tu, fl.tu_rows, fl.tu_stride = F['Tu'].data_ptr(), node_rows.data_ptr(), node_rows.shape[1]
-            if self.proj[i + 1] is not None:
+            if self.proj[i + 1] is not None and self.jk is not None:
+                J = self.jk[i + 1]
+                fl.pool, fl.jk_kind, fl.jk_act = (2 if mean else 1), J['kind'], J['act']
+                fl.jk_W1, fl.jk_b1 = J['W1'].data_ptr(), J['b1'].data_ptr()
+                if J['kind'] == 2:
+                    fl.jk_W0T, fl.jk_vec = J['W0T'].data_ptr(), J['vec'].data_ptr()
+                pooled_list.append(None)
+            elif self.proj[i + 1] is not None:
                 pooled = torch.empty((G, D), dtype=torch.float32, device=dev)
                 fl.pool, fl.pooled = (2 if mean else 1), pooled.data_ptr()
                 d_up = L['U2'].shape[0]
@@ -242,10 +279,14 @@ class FusedModel(FusedForward):
             fm.x0, fm.x0_ld, fm.x0_d = x0.data_ptr(), x0.stride(0), x0.shape[1]
         fm.N, fm.E, fm.G = N, E, G
         fm.status = self.status.data_ptr()
+        out = None
+        if self.jk is not None:
+            out = torch.empty((G, self.n_out), dtype=torch.float32, device=dev)
+            fm.out, fm.n_out = out.data_ptr(), self.n_out
         with torch.cuda.device(dev):
             _lib.call('fused_model', 'gsn_fused_model_fwd', ctypes.byref(fm), _lib.stream_ptr())
         self._keep = keep
-        return self._project(pooled_list)
+        return out if out is not None else self._project(pooled_list)
 
     def raise_on_status(self):
         bits = (int(self.status.item()) if getattr(self, 'status', None) is not None else 0) & _lib.S_FATAL

@@ -392,6 +392,12 @@ typedef struct GsnFusedLayer {
     const int32_t *d_edge_rows; const float *d_Te;
     const float *d_vec; float *d_pooled; float *d_x_out;
     int32_t n_node_cols, tu_stride, n_edge_cols, te_rows, has_dense, mat0, act_msg, act_upd, act_out, pool;
+    /* JK head of this layer's readout, evaluated in the kernel (models_graph_classification.py:236-240; jk_kind 0 = not
+     * here, the caller projects d_pooled): 1 = Linear: out += pooled W1^T + b1;  2 = mlp (models_misc.py:52-59, eval-mode
+     * BatchNorm folded): out += act((pooled W0^T + b0) s + t) W1^T + b1.   d_jk_W0T fp32 [D, D] = W0 transposed (k-major),
+     * d_jk_vec fp32 [3, D] = b0, s, t; d_jk_W1 fp32 [n_out, D]; d_jk_b1 fp32 [n_out]; zero padding as for the layers. */
+    const float *d_jk_W0T; const float *d_jk_vec; const float *d_jk_W1; const float *d_jk_b1;
+    int32_t jk_kind, jk_act;
 } GsnFusedLayer;
 typedef struct GsnFusedModel {
     GsnFusedLayer layers[GSN_FUSED_MAX_LAYERS];
@@ -403,7 +409,8 @@ typedef struct GsnFusedModel {
     int32_t *d_status;
     const int32_t *d_tile_plan;   /* optional (gsn_tile_plan): one CTA per tile instead of graphs_per_unit graphs per CTA */
     int32_t max_tiles;            /* capacity the plan was built with */
-    int32_t _pad;
+    int32_t n_out;                /* columns of d_out (<= 32) when any layer has jk_kind != 0 */
+    float *d_out;                 /* fp32 [G, n_out]: sum of the in-kernel JK projections (every row is written) */
 } GsnFusedModel;
 int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream);
 /*

@@ -176,6 +176,24 @@ def test_tile_plan_greedy_packing():
     assert torch.equal(out_plan, out_unit)
 
 
+@pytest.mark.parametrize('name', ['zinc_gsnv_general', 'zinc_gsne_general', 'sr_general_local_nobn', 'mpnn_general'])
+def test_jk_head_in_kernel_vs_projection_launches(name, monkeypatch):
+    """the JK head (models_graph_classification.py:236-240) evaluated inside the model kernel equals the pooled rows
+    projected by separate GEMM launches"""
+    from gsn_b200 import fused_model
+    model, b, ref = _golden_model(name)
+    outs = []
+    for flag in (True, False):
+        monkeypatch.setattr(fused_model, 'JK_IN_KERNEL', flag)
+        fm = fused_model.FusedModel(model)
+        outs.append(fm(b).clone())
+        fm.raise_on_status()
+        assert (fm.jk is not None) == (flag and fm.proj[0] is None)
+    scale = max(float(ref.abs().max()), 1.0)
+    torch.testing.assert_close(outs[0], outs[1], atol=TOL * scale, rtol=TOL)
+    torch.testing.assert_close(outs[0].cpu(), ref, atol=TOL * scale, rtol=TOL)
+
+
 def test_one_kernel_rejects_oversized_graphs():
     from gsn_b200 import fused_model
     model, b, _ = _golden_model('zinc_gsne_general')
