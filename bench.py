@@ -331,9 +331,19 @@ def run_ours(args, rank, world, local_rank):
         prof = instrumented(pipe, dev_in, max(5, min(args.steps, 10)))
         kernels_us = {k: round(v[0] * 1e6, 2) for k, v in prof.items()}
 
+        fmod = pipe.fused
+        w_bytes = int(fmod.Whi.numel() * 2 * 2 + sum(F['vec'].numel() * 4 + sum(F[k].numel() * 4 for k in ('Tn', 'Te', 'Tu')
+                                                                               if F[k] is not None) for F in fmod.fm_layers))
+        d_id_local = int(sum(encoder.d))
+
         def forward_roofline(n, e, g, t_fm):
             fl = FLOPS_PER_NODE * n
-            by = 4 * n + 4 * e * 2 + 8 * (g + 1) + 4 * (n + 1) + 4 * e + 4 * g * D_OUT      # index inputs + CSR in, pooled rows out
+            # the kernel's own operands: index inputs + CSR in, weights / tables once, predictions out
+            by = 4 * n + 4 * e * 2 + 8 * (g + 1) + 4 * (n + 1) + 4 * e + 4 * g + w_bytes
+            # every tensor at the reference's layer boundary once (one-hot x / identifiers / bond types as the
+            # fp32 tensors the reference materialises, x in and out of every layer, edge_index 16 B per edge)
+            by_8d = (4 * n * 28 + 4 * e * d_id_local + 4 * e * 4 + 16 * e + 4 * n * D_OUT) + \
+                    (N_LAYERS - 1) * (4 * n * D_OUT + 4 * e * 4 + 16 * e + 4 * n * D_OUT) + w_bytes // 2
             return {'bound': 'tensor',
                     'kernel': 'fused_model_kernel<128> (gsn_fused_model_fwd): all layers of the model for a tile of whole graphs; '
                               'the dominant launch of a step',
@@ -343,13 +353,23 @@ def run_ours(args, rank, world, local_rank):
                     'avg_launch_us': t_fm * 1e6,
                     'hbm_view': {'algorithmic_bytes_per_launch': by, 'GBps': by / t_fm / 1e9, 'frac_of_hbm_peak': by / t_fm / 1e9 / hbm_peak,
                                  'peak': hbm_peak, 'peak_source': hbm_src,
-                                 'note': 'the kernel reads index columns + CSR and writes pooled rows only: activations never '
-                                         'leave the SM, so HBM is not what bounds it'},
+                                 'note': 'the kernel reads index columns + CSR + weights and writes the predictions only: '
+                                         'activations never leave the SM, so HBM is not what bounds it'},
+                    'survey_8d_view': {'algorithmic_bytes_per_launch': by_8d, 'GBps': by_8d / t_fm / 1e9,
+                                       'frac_of_hbm_peak': by_8d / t_fm / 1e9 / hbm_peak,
+                                       'note': 'SURVEY 8(d) numerator: the tensors of the reference layer API read / written once '
+                                               'per layer; the one-kernel forward does not move them at all'},
                     'how': 'median device time of the launch (CUDA events on the launching stream, L2 flushed before every step) '
                            'in an eager pass over the step; algorithmic flops = FLOPS_PER_NODE x nodes (fp32-equivalent; the '
                            'tensor cores execute 3 fp16 MMAs per product, mma_* counts those)'}
         roof = forward_roofline(N0, E0, G, prof['fused_model'][0])
-        roof['traffic'] = None
+        traffic = {}
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r2_ncu_traffic.json')) as f:
+                traffic = json.load(f)['bytes_per_launch']
+        except Exception:
+            pass
+        roof['traffic'] = traffic.get(str(B))            # ncu dram bytes of this kernel at this batch size (committed capture)
         roof['launches_per_step'] = prof['fused_model'][1]
         sweep = []
         roof_large = None
@@ -382,6 +402,7 @@ def run_ours(args, rank, world, local_rank):
                     if Bs == 131072:
                         roof_large = forward_roofline(n_s, e_s, Bs, pr['fused_model'][0])
                         roof_large['batch'] = Bs
+                        roof_large['traffic'] = traffic.get(str(Bs))
                     del tens
                     torch.cuda.empty_cache()
                 except Exception as ex:      # the sweep is informative only; never lose the headline line
