@@ -57,7 +57,7 @@ _SIGNATURES = {
     'gsn_encode_rows': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     'gsn_encode_rows_grouped': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     'gsn_dgn_aggregate_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32,
-                                             ctypes.c_float, _vp, _vp]),
+                                             ctypes.c_float, _vp, _vp, _vp]),
     'gsn_dgn_aggregate_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32,
                                              ctypes.c_float, _vp, _vp, _vp, _vp]),
 }

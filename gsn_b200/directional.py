@@ -82,11 +82,14 @@ class _DgnAggregate(torch.autograd.Function):
         arr = _aggr_array(aggr, Fn, Fe)
         sc = (ctypes.c_int32 * len(scalers))(*scalers)
         out = torch.empty((N, len(aggr) * len(scalers) * d), dtype=torch.float32, device=h.device)
+        # per-edge weights of the directional aggregators (four at a time): workspace of the call, caller-allocated
+        n_dir = sum(1 for k, _, _ in aggr if k >= KIND['dir-av'])
+        scratch = torch.empty(4 * max(plan.E, 1), dtype=torch.float32, device=h.device) if n_dir > 0 else None
         with torch.cuda.device(h.device):
             _lib.call('dgn_aggregate', 'gsn_dgn_aggregate_fwd', _lib.ptr(plan.rowptr), _lib.ptr(plan.eid), _lib.ptr(plan.nbr),
                       N, plan.E, _lib.ptr(h), d, _lib.ptr(nf), Fn, _lib.ptr(ef), Fe, ctypes.cast(arr, ctypes.c_void_p),
                       len(aggr), ctypes.cast(sc, ctypes.c_void_p), len(scalers), ctypes.c_float(avg_log), _lib.ptr(out),
-                      _lib.stream_ptr())
+                      _lib.ptr(scratch), _lib.stream_ptr())
         ctx.save_for_backward(h)
         ctx.rest = (plan, nf, ef, list(aggr), list(scalers), avg_log)
         return out

@@ -434,6 +434,9 @@ int gsn_tile_plan(const int64_t *d_node_ptr, int64_t G, int32_t *d_tile_plan, in
  *   out[i, s*(A*d) + a*d + c] = scaler_s( aggregator_a( {h[j,c]}, vector_field, h[i,c] ) )
  * Nodes without in-edges get zeros (DGL leaves rows that receive no message zero-filled).  With n_scalers == 1 no
  * scaling is applied whatever the scaler is (dgn_layer.py:50-51).  avg_log = avg_d["log"] of the training set.
+ * d_scratch: 4 * E floats (per-edge weights of up to four directional aggregators at a time; may be NULL when the list
+ * holds none).  Launches: per group of four directional aggregators one weight kernel (thread per node) + one aggregation
+ * kernel (thread per node and 4-channel chunk, one pass over the in-edges).
  */
 #define GSN_DGN_MEAN 0
 #define GSN_DGN_SUM 1
@@ -460,7 +463,7 @@ typedef struct GsnDgnAggr {
 int gsn_dgn_aggregate_fwd(const int32_t *d_rowptr, const int32_t *d_eid, const int32_t *d_nbr, int64_t N, int64_t E,
                           const float *d_h, int32_t d, const float *d_node_field, int32_t Fn, const float *d_edge_field,
                           int32_t Fe, const GsnDgnAggr *h_aggr, int32_t n_aggr, const int32_t *h_scalers,
-                          int32_t n_scalers, float avg_log, float *d_out, void *stream);
+                          int32_t n_scalers, float avg_log, float *d_out, float *d_scratch, void *stream);
 /* Backward w.r.t. h (autograd of aggregators.py:8-69; the fields are data).  Per in-edge k (j -> i) the gradient that
  * flows to h[j] is written to d_M[eid[k], 0:d] (edge-id order, [E, d]) and the gradient to the node's own row (dx kinds)
  * to d_SG [N, d]:  grad_h = d_SG + gsn_mp_segment_sum(plan grouped by edge_index[0], d_M).  Deterministic. */
