@@ -53,6 +53,7 @@ _SIGNATURES = {
     'gsn_mp_ogb_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     'gsn_fused_model_fwd': (ctypes.c_int, [_vp, _vp]),
     'gsn_tile_plan': (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int32, _vp, _vp]),
+    'gsn_submit_step': (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_size_t, _vp, _vp, ctypes.c_size_t, _vp]),
     'gsn_pool_ptr': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     'gsn_encode_rows': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     'gsn_encode_rows_grouped': (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -70,6 +70,7 @@ class GSNPipeline:
         self.encoder, self.max_nodes = encoder, int(max_nodes_per_graph)
         self.n_cols = total_columns(subgraph_dicts)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._exec = None               # cudaGraphExec_t of the captured step (gsn_submit_step)
         self._static: Dict[str, torch.Tensor] = {}
         self._out: Optional[torch.Tensor] = None
         self.last_status: Optional[torch.Tensor] = None
@@ -133,7 +134,7 @@ class GSNPipeline:
                 self.step(self._static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
+        self._graph, self._exec = torch.cuda.CUDAGraph(), None
         with torch.no_grad(), torch.cuda.graph(self._graph):
             self._out = self.step(self._static)
         return self
@@ -146,6 +147,25 @@ class GSNPipeline:
     def replay(self) -> torch.Tensor:
         self._graph.replay()
         return self._out
+
+    def submit(self, stream: torch.cuda.Stream, d_in: Optional[torch.Tensor] = None, src: Optional[torch.Tensor] = None,
+               out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The captured step on `stream` through ONE native call (`gsn_submit_step`): copy `src` (pinned host or device)
+        into the static input buffer `d_in`, replay, copy the predictions into `out_host` (pinned).  Same effect as
+        `d_in.copy_(src); replay(); out_host.copy_(out)` under `torch.cuda.stream(stream)` at a fraction of the host time."""
+        from . import _lib
+        out = self._out
+        nin = 0 if src is None else src.numel() * src.element_size()
+        nout = 0 if out_host is None else out_host.numel() * out_host.element_size()
+        if out_host is not None and nout > out.numel() * out.element_size():
+            raise ValueError('out_host is larger than the step\'s output')
+        if self._exec is None:
+            self._exec = self._graph.raw_cuda_graph_exec()
+        _lib.check(_lib.lib().gsn_submit_step(self._exec, None if d_in is None else d_in.data_ptr(),
+                                              None if src is None else src.data_ptr(), nin,
+                                              None if out_host is None else out_host.data_ptr(), out.data_ptr(), nout,
+                                              stream.cuda_stream), 'gsn_submit_step')
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -281,3 +301,10 @@ class BucketedPipeline:
         pipe, pk, buf = self._lru[key]
         buf.copy_(packed, non_blocking=True)
         return pipe.replay()[:n_graphs]
+
+    def submit(self, key, packed: torch.Tensor, n_graphs: int, stream: torch.cuda.Stream,
+               out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """run() on an explicit stream through one native call (copy in, replay, optional copy of the first
+        `out_host.numel()` predictions to pinned host memory); see GSNPipeline.submit"""
+        pipe, pk, buf = self._lru[key]
+        return pipe.submit(stream, buf, packed, out_host)[:n_graphs]

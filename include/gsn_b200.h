@@ -423,6 +423,16 @@ int gsn_fused_model_fwd(const GsnFusedModel *h_m, void *stream);
 int gsn_tile_plan(const int64_t *d_node_ptr, int64_t G, int32_t *d_tile_plan, int32_t max_tiles, int32_t *d_status,
                   void *stream);
 
+/*
+ * Submission of one captured step on `stream` (host side only; see csrc/runtime.cu): copy in_bytes from src (pinned host
+ * or device) into the captured step's static input buffer d_in, launch graph_exec (a cudaGraphExec_t, e.g.
+ * torch.cuda.CUDAGraph.raw_cuda_graph_exec()), then copy out_bytes of the static output d_out to pinned host memory h_out.
+ * in_bytes == 0 / out_bytes == 0 skip the copies.  Replaces the per-step body of the reference's evaluation loop
+ * (train_test_funcs.py:190-215: `data.to(device)`, `model(data)`, `.cpu()`) for a captured step.
+ */
+int gsn_submit_step(void *graph_exec, void *d_in, const void *src, size_t in_bytes, void *h_out, const void *d_out,
+                    size_t out_bytes, void *stream);
+
 /* ------------------------------------------------------------------ */
 /* DGN consumer of COUNT (directional_gsn/)                            */
 /* ------------------------------------------------------------------ */

@@ -42,7 +42,10 @@ def main():
     ei = torch.from_numpy(b['edge_index']).to(dev)
     ptr = torch.from_numpy(b['node_ptr'])
     N, E = int(b['node_ptr'][-1]), int(ei.shape[1])
+    import bench
     out = {}
+    clk = bench.Clocks(local)
+    clk.__enter__()
     for scope in ('global', 'local'):
         sds = patterns.make_subgraph_dicts(els, scope)
         ids = counting.count_batch(ei, ptr, sds, False, scope, max_nodes_per_graph=64)          # warm-up + result
@@ -88,6 +91,7 @@ def main():
                       'general_path_seconds_build_plus_count': float(t[0]), 'general_path_seconds_count_kernels': float(t[1]),
                       'general_path_graphs_per_s': per_rank * world / float(t[0]),
                       'columns': a.k - 2, 'checksum': int(ids.sum().item())}
+    clk.__exit__()
     if rank == 0:
         bytes_alg = 16 * E + 8 * N * (a.k - 2)
         print(json.dumps({'config': f'{per_rank * world} synthetic graphs (mean 30 nodes, {per_rank} per GPU, '
@@ -95,7 +99,7 @@ def main():
                           'n_gpus': world, 'N_per_gpu': N, 'E_per_gpu': E, 'vertex_scope': out['global'],
                           'edge_scope': out['local'],
                           'hbm_fraction_vertex_scope': bytes_alg / out['global']['seconds'] / 1e9 / 6539.5,
-                          'oracle_checked_graphs': a.check}), flush=True)
+                          'oracle_checked_graphs': a.check, 'clocks': clk.summary()}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -71,6 +71,9 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t[0])
 
+    import bench
+    clk = bench.Clocks(int(os.environ.get('LOCAL_RANK', 0)))
+    clk.__enter__()
     ids = counting.count_batch(ei_t, ptr_t, sds, False, 'local', max_nodes_per_graph=max_n)
     ok = bool(np.array_equal(ids.cpu().numpy(), shard['gold']))
     t_count = timed(lambda: counting.count_batch(ei_t, ptr_t, sds, False, 'local', max_nodes_per_graph=max_n, check=False), a.reps)
@@ -105,13 +108,15 @@ def main():
             for b in small:
                 model(b)
         t_small = timed(run_small, a.reps) / max(len(small), 1)
+    clk.__exit__()
     if rank == 0:
         E_tot = int(edge_ptr[-1])
         print(json.dumps({'config': 'IMDB-BINARY fixture, 1000 graphs, cliques k<=5 edge scope + README.md:99 model (gin, local)',
                           'n_gpus': world, 'count_bit_exact_vs_graph_tool_fixture': ok, 'id_vocab': enc.d,
                           'count_seconds': t_count, 'count_graphs_per_s': 1000 / t_count, 'count_edges_per_s': E_tot / t_count,
                           'forward_all_graphs_seconds': t_full, 'forward_all_graphs_per_s': 1000 / t_full,
-                          'forward_b32_seconds_per_batch': t_small, 'forward_b32_graphs_per_s': 32 * world / t_small}), flush=True)
+                          'forward_b32_seconds_per_batch': t_small, 'forward_b32_graphs_per_s': 32 * world / t_small,
+                          'clocks': clk.summary()}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

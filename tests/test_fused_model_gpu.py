@@ -234,3 +234,13 @@ def test_bucketed_pipeline_variable_shapes():
     # padding never leaks: a batch alone and the same batch after another one of the bucket give identical bits
     for a, b_ in zip(outs[:len(raws)], outs[len(raws):]):
         assert torch.equal(a, b_)
+    # submit(): the same step through one native call on an explicit stream, inputs from pinned host memory,
+    # predictions read back to pinned host memory
+    st = torch.cuda.Stream()
+    for i, b in enumerate(raws[:3]):
+        key, packed, G = bp.prepare(b, dev, pin=True)
+        host = torch.empty((G, outs[i].shape[1]), dtype=torch.float32).pin_memory()
+        st.wait_stream(torch.cuda.current_stream())
+        got = bp.submit(key, packed, G, st, host)
+        st.synchronize()
+        assert torch.equal(host, outs[i].cpu()) and torch.equal(got.cpu(), host)
