@@ -42,6 +42,7 @@ if ROOT not in sys.path:
 
 K_MAX = 8
 D_OUT = 128
+REGION_REPEATS = 3      # timed regions per reported number (median)
 N_LAYERS = 4
 
 
@@ -283,10 +284,12 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         ms_single = sum(a.elapsed_time(b) for a, b in evs) / args.steps
         # ---- value: whole-job throughput with S steps on different batches in flight (S streams), inputs resident in HBM
-        ms_total = timed_region(pool_dev, False)
+        # each region = W warm-up steps + exactly K timed steps; a K = 50 region lasts 1.5 ms, so it is repeated and the MEDIAN
+        # region is reported (max over ranks of one 1.5 ms region at 8 processes measured one rank's scheduling hiccup)
+        ms_total = float(np.median([timed_region(pool_dev, False) for _ in range(REGION_REPEATS)]))
         # ---- e2e: every step's inputs come from PINNED HOST memory (H2D inside the region) and its predictions are read
         # back to the host (D2H inside the region); same S streams
-        ms_e2e = timed_region(pool_host, True)
+        ms_e2e = float(np.median([timed_region(pool_host, True) for _ in range(REGION_REPEATS)]))
         assert bool(torch.isfinite(out_host[:args.steps]).all())
     h2d = int(np.mean([t.numel() for t in pool_host]))
     d2h = out_host[0].numel() * out_host.element_size()
@@ -437,6 +440,7 @@ def run_ours(args, rank, world, local_rank):
                        'shapes': f'variable (N, E) per batch, padded to {n_buckets} shape buckets (node step 128, edge step 256); '
                                  f'one captured CUDA graph per (stream, bucket)',
                        'cuda_graph': True, 'streams': S, 'pool': P, 'buckets': n_buckets,
+                       'timed_regions': f'{REGION_REPEATS} regions of W warm-up + K timed steps each, median region reported',
                        'parallelism': f'batch-sharded x{world}, no data-path collective'},
             'edges_per_s': world * E_mean / (ms_per_step * 1e-3),
             'single_stream': {'ms_per_step': ms_single, 'graphs_per_s': world * G / (ms_single * 1e-3),
@@ -446,7 +450,8 @@ def run_ours(args, rank, world, local_rank):
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(my_launches_per_step) * args.steps,     # our kernels; + 1 packed input copy per step
             'gpu_launches_per_step': int(my_launches_per_step),
-            'host_enqueue_us_per_step': {'value': host_enqueue_us[0], 'e2e': host_enqueue_us[1],
+            'host_enqueue_us_per_step': {'value': float(np.median(host_enqueue_us[:REGION_REPEATS])),
+                                         'e2e': float(np.median(host_enqueue_us[REGION_REPEATS:])),
                                          'note': 'host time to enqueue a step (BucketedPipeline.submit = one native call: packed copy + graph launch [+ read-back]) in the two timed regions'},
             'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep,
             'scatter_kernels': scatter_kernels, 'roofline_large_batch': roof_large, 'torch_eager_gpu': eager, 'gsn_v': gsn_v,
