@@ -91,6 +91,29 @@ def test_random_batches_vs_oracle(family, scope_name, induced, graphlet_patterns
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize('family', ['cliques5', 'cycles5', 'graphlets4'])
+@pytest.mark.parametrize('scope_name', ['global', 'local'])
+def test_dense_batches_vs_oracle(family, scope_name, graphlet_patterns):
+    """average degree >= 8: heavy items are deferred to count_heavy_kernel (one warp per clique item, 128 shares per item
+    otherwise), graphs of <= 64 vertices run with one-word sets inside a batch laid out for a 70-vertex graph"""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f'dense/{family}/{scope_name}'.encode()))
+    # k <= 5 / graphlets up to 4 vertices: the all-maps oracle on dense graphs
+    els = {'cliques5': lambda: FAMILIES['cliques5'](graphlet_patterns), 'cycles5': lambda: FAMILIES['cycles8'](graphlet_patterns)[:3],
+           'graphlets4': lambda: graphlet_patterns[3] + graphlet_patterns[4]}[family]()
+    graphs = []
+    for _ in range(14):
+        n = int(rng.integers(12, 23))
+        graphs.append((random_graph(rng, n, float(rng.uniform(0.6, 0.95))), n))
+    graphs.append((random_graph(rng, 70, 0.25), 70))         # forces W = 2, itself dense enough for heavy items
+    node_ptr, edge_ptr, ei = batch_graphs(graphs)
+    assert ei.shape[1] / node_ptr[-1] >= 8
+    scope = 1 if scope_name == 'local' else 0
+    exp = count_c.count_batch(node_ptr, edge_ptr, ei, count_vf2.make_subgraph_dicts(els, scope_name), False, scope)
+    got = _cuda_ids(node_ptr, ei, _dicts(els, scope_name), False, scope_name)
+    assert np.array_equal(got, exp)
+
+
 def test_single_graph_api_matches_reference_semantics():
     """count_fn(edge_index, subgraph_dict=, induced=, num_nodes=) as called at utils_ids.py:24"""
     from gsn_b200 import counting, patterns
