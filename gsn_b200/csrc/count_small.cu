@@ -21,6 +21,15 @@
 
 namespace gsn {
 
+// Build-flag-only profiling aid (python -m gsn_b200.build --profile): clock64 stamps of the phases of every CTA, [block][8]
+// (first 256 blocks).  Not compiled into the shipped library.
+#ifdef GSN_PROFILE_STAMPS
+__device__ long long g_cs_stamps[256 * 8];
+#define CS_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_cs_stamps[blockIdx.x * 8 + (i)] = clock64(); } while (0)
+#else
+#define CS_STAMP(i) do { } while (0)
+#endif
+
 struct CsParams {
     const int64_t *src, *dst;
     int64_t E;
@@ -271,6 +280,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
     const int C = P.n_cols;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
+    CS_STAMP(0);
 
     // ---- chunk: graphs whose first node lies in [blockIdx * T, (blockIdx + 1) * T)
     {
@@ -315,6 +325,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
         for (int v = a; v < b; ++v) goff[v] = (uint16_t)a;
     }
     __syncthreads();
+    CS_STAMP(1);          // searches + graph offsets done
     const int64_t e0 = sh_e[0], e1 = sh_e[1];
 
     // edge (a, b) of the segment -> chunk-local a and graph-local b, or -1 when it contributes nothing
@@ -367,6 +378,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
         }
     }
     __syncthreads();
+    CS_STAMP(2);          // adjacency + slot offsets built
     int64_t *outc = prm.out + P.col0;
 
     // ---- passes: vertex scope = the whole chunk; edge scope = runs of graphs whose slots fit the edge_dict capacity
@@ -425,6 +437,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
         }
         __syncthreads();
 
+        CS_STAMP(3);      // pass set-up + edge_dict done
         CsAcc acc{in_smem ? sacc : nullptr, colmap, outc, prm.out_ld, v0, prm.status, C, ps0};
         if (P.scope == 0) acc.sbase = 0;
         // vertex-scope rows are chunk-local nodes relative to the pass start
@@ -453,6 +466,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
             }
         }
         __syncthreads();
+        CS_STAMP(4);      // search done (all warps)
         // ---- write-out
         if (in_smem) {
             if (P.scope == 0) {
@@ -475,6 +489,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
             }
         }
         __syncthreads();
+        CS_STAMP(5);      // write-out done
         pn0 = pn1;
         pg = pg1;
     }
@@ -492,6 +507,13 @@ static int cs_launch(const CsParams &prm, int64_t chunks, size_t smem, cudaStrea
 }  // namespace gsn
 
 using namespace gsn;
+
+#ifdef GSN_PROFILE_STAMPS
+extern "C" int gsn_cs_profile_read(long long *h_out) {
+    GSN_CUDA_OK(cudaMemcpyFromSymbol(h_out, g_cs_stamps, sizeof(long long) * 256 * 8));
+    return GSN_OK;
+}
+#endif
 
 extern "C" int gsn_count_small(const int64_t *d_edge_index, int64_t E, const int64_t *d_node_ptr, int64_t G, int64_t N,
                                const GsnPlan *h_plan, int64_t *d_out, int64_t out_ld, int32_t *d_status, void *stream_) {
