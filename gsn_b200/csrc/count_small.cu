@@ -116,12 +116,22 @@ __device__ __forceinline__ uint64_t bits_lt(int v) { return (1ull << v) - 1ull; 
 // frame: q0 = {cand.lo, cand.hi, X.lo, X.hi}, q1 = {path.lo, path.hi, meta, -}
 //   meta = depth p (4 bits) | graph offset in the chunk (16 bits) << 4 | f0 << 20 | f1 << 26 ; path = f[2..] 6 bits each
 //   X = vertices of the path (non-induced) or the union of adj(f[q]), 1 <= q <= p (induced: chords)
-template <bool INDUCED>
+// The per-warp stack is sorted by depth, deepest on top.  A step takes frames from the top until they hold 32 candidates
+// (prefix sum over the top 32 frames) and every lane extends ONE (frame, candidate) pair -- a frame with c candidates is
+// consumed in one step, not in c: the critical path of a root is its depth, not the sum of its branching factors (clock64
+// stamps at B = 128: the slowest warp of a CTA searched 4x longer than the first one to finish with one candidate per frame
+// and step).  Children are pushed in reverse lane order (the window is read deepest first, so that keeps the stack sorted
+// without a pass per depth), a partially consumed frame goes back below them, new roots are inserted at the bottom.
+// Every level holds <= 32 frames: a level-d frame is created only in a step whose window reaches level d-1, i.e. one that
+// consumes every older level-d frame -> size <= 32 * (kmax - 2).
+template <bool INDUCED, int SCOPE>
 __device__ void cycles_warp(const GsnPlan &P, const uint64_t *adj, const int32_t *rp, const uint16_t *goff, int sn0, int sn1,
                             int *ticket, uint4 *stack, int frame_cap, CsAcc &acc, int nwarps) {
     const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     const unsigned lt = (1u << lane) - 1u;
-    const int kmin = P.kmin, kmax = P.kmax, scope = P.scope;
+    const int kmin = P.kmin, kmax = P.kmax;
+    constexpr int scope = SCOPE;
     int size = 0;
     bool seeds_left = true;
     while (true) {
@@ -130,12 +140,12 @@ __device__ void cycles_warp(const GsnPlan &P, const uint64_t *adj, const int32_t
             int base = 0, take = 0;
             if (lane == 0) {
                 const int remaining = sn1 - *(volatile int *)ticket;
-                take = remaining > 0 ? remaining / (2 * nwarps) + 1 : 1;
+                take = remaining > 0 ? remaining / (4 * nwarps) + 1 : 1;
                 if (take > 32 - size) take = 32 - size;
                 base = atomicAdd(ticket, take);
             }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            take = __shfl_sync(0xffffffffu, take, 0);
+            base = __shfl_sync(FULL, base, 0);
+            take = __shfl_sync(FULL, take, 0);
             if (base >= sn1) seeds_left = false;
             const int node = base + lane;
             bool ok = lane < take && node < sn1;
@@ -147,43 +157,80 @@ __device__ void cycles_warp(const GsnPlan &P, const uint64_t *adj, const int32_t
                 cand = adj[node] & bits_gt(f0);
                 ok = cand != 0 && kmax >= 3;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const int pos = size + __popc(m & lt);
-                const uint64_t X = INDUCED ? 0ull : (1ull << f0);
-                stack[2 * pos] = make_uint4((uint32_t)cand, (uint32_t)(cand >> 32), (uint32_t)X, (uint32_t)(X >> 32));
-                stack[2 * pos + 1] = make_uint4(0u, 0u, (uint32_t)(0 | (go << 4) | (f0 << 20)), 0u);
+            const unsigned m = __ballot_sync(FULL, ok);
+            const int nnew = __popc(m);
+            if (nnew) {
+                // roots are the shallowest frames: they go to the bottom, the (< 32) frames of the stack move up
+                uint4 a0, a1;
+                if (lane < size) { a0 = stack[2 * lane]; a1 = stack[2 * lane + 1]; }
+                __syncwarp();
+                if (lane < size) { stack[2 * (lane + nnew)] = a0; stack[2 * (lane + nnew) + 1] = a1; }
+                if (ok) {
+                    const int pos = __popc(m & lt);
+                    const uint64_t X = INDUCED ? 0ull : (1ull << f0);
+                    stack[2 * pos] = make_uint4((uint32_t)cand, (uint32_t)(cand >> 32), (uint32_t)X, (uint32_t)(X >> 32));
+                    stack[2 * pos + 1] = make_uint4(0u, 0u, (uint32_t)(0 | (go << 4) | (f0 << 20)), 0u);
+                }
+                size += nnew;
+                __syncwarp();
             }
-            size += __popc(m);
-            __syncwarp();
             if (size == 0) {
                 if (!seeds_left) break;
                 continue;
             }
         }
         if (size == 0) break;
+        // ---- the window: the top <= 32 frames, deepest first; prefix sum of their candidate counts
         const int n = size < 32 ? size : 32;
-        const bool active = lane < n;
-        bool keep = false, child = false;
-        uint4 kq0, kq1, cq0, cq1;
-        if (active) {
-            const int idx = size - 1 - lane;
-            kq0 = stack[2 * idx];
-            kq1 = stack[2 * idx + 1];
+        const int top = size - 1;
+        uint4 wq0 = make_uint4(0u, 0u, 0u, 0u), wq1 = wq0;
+        int cnt = 0;
+        if (lane < n) {
+            wq0 = stack[2 * (top - lane)];
+            wq1 = stack[2 * (top - lane) + 1];
+            cnt = __popc(wq0.x) + __popc(wq0.y);
         }
-        __syncwarp();
-        size -= n;
+        int pre = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, pre, o);
+            if (lane >= o) pre += t;
+        }
+        const int total = __shfl_sync(FULL, pre, 31);
+        const int excl = pre - cnt;
+        const int m_taken = __popc(__ballot_sync(FULL, lane < n && excl < 32));      // frames touched by this step
+        const int work = total < 32 ? total : 32;
+        // the last touched frame may keep candidates: it returns to the stack without the ones handed out now
+        bool keep = false;
+        uint4 kq0 = wq0;
+        if (lane == m_taken - 1 && pre > 32) {
+            uint64_t c = (uint64_t)wq0.x | ((uint64_t)wq0.y << 32);
+            for (int i = excl; i < 32; ++i) c &= c - 1;
+            kq0.x = (uint32_t)c;
+            kq0.y = (uint32_t)(c >> 32);
+            keep = true;
+        }
+        // ---- lane t extends candidate t of the window: frame f = number of frames with pre <= t, k-th candidate of it
+        int f = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int pv = __shfl_sync(FULL, pre, f + step - 1);
+            if (pv <= lane) f += step;
+        }
+        f &= 31;
+        const int pf = __shfl_sync(FULL, pre, f), cf = __shfl_sync(FULL, cnt, f);
+        const bool active = lane < work;
+        bool child = false;
+        uint4 cq0, cq1;
         if (active) {
-            uint64_t cand = (uint64_t)kq0.x | ((uint64_t)kq0.y << 32);
-            const uint64_t X = (uint64_t)kq0.z | ((uint64_t)kq0.w << 32);
-            uint64_t path = (uint64_t)kq1.x | ((uint64_t)kq1.y << 32);
-            uint32_t meta = kq1.z;
+            const int k = lane - (pf - cf);
+            const uint4 q0 = stack[2 * (top - f)], q1 = stack[2 * (top - f) + 1];
+            const int c_lo = __popc(q0.x);
+            const int j = k < c_lo ? (int)__fns(q0.x, 0, k + 1) : 32 + (int)__fns(q0.y, 0, k - c_lo + 1);
+            const uint64_t X = (uint64_t)q0.z | ((uint64_t)q0.w << 32);
+            uint64_t path = (uint64_t)q1.x | ((uint64_t)q1.y << 32);
+            uint32_t meta = q1.z;
             const int p = meta & 15, go = (meta >> 4) & 0xFFFF, f0 = (meta >> 20) & 63;
-            const int j = __ffsll((long long)cand) - 1;
-            cand &= cand - 1;
-            keep = cand != 0;
-            kq0.x = (uint32_t)cand;
-            kq0.y = (uint32_t)(cand >> 32);
             // ---- child: the path extended by j
             const int pc = p + 1;
             if (pc == 1) meta = (meta & ~(63u << 26)) | ((uint32_t)j << 26);
@@ -241,37 +288,31 @@ __device__ void cycles_warp(const GsnPlan &P, const uint64_t *adj, const int32_t
                 cq1 = make_uint4((uint32_t)path, (uint32_t)(path >> 32), meta, 0u);
             }
         }
-        // ---- push back, keeping the stack sorted by depth (deepest on top): the top 32 frames are then always the
-        //      deepest ones, every popped level refills itself with at most as many frames as were taken from the level
-        //      above it, and no level ever holds more than 32 frames -> size <= 32 * (kmax - 2)
-        const int myp = active ? (int)(kq1.z & 15) : 99;
-        const int dmin = __reduce_min_sync(0xffffffffu, (unsigned)myp);
-        const int dmax = __reduce_max_sync(0xffffffffu, active ? (unsigned)(kq1.z & 15) : 0u);
-        int pos = size;
-        for (int d = dmin; d <= dmax + 1; ++d) {
-            const bool k_here = keep && myp == d, c_here = child && myp + 1 == d;
-            const unsigned mk = __ballot_sync(0xffffffffu, k_here), mc = __ballot_sync(0xffffffffu, c_here);
-            if (k_here) {
-                const int at = pos + __popc(mk & lt);
-                if (at < frame_cap) { stack[2 * at] = kq0; stack[2 * at + 1] = kq1; }
-            }
-            pos += __popc(mk);
-            if (c_here) {
-                const int at = pos + __popc(mc & lt);
-                if (at < frame_cap) { stack[2 * at] = cq0; stack[2 * at + 1] = cq1; }
-            }
-            pos += __popc(mc);
-        }
-        if (pos > frame_cap) {           // cannot happen (bound above); never write outside the stack
+        // ---- pop the touched frames, push [kept frame] [children, deepest on top]
+        __syncwarp();                                   // every read of the window is done
+        size -= m_taken;
+        const unsigned mk = __ballot_sync(FULL, keep), mc = __ballot_sync(FULL, child);
+        const int nkeep = mk ? 1 : 0, nchild = __popc(mc);
+        if (size + nkeep + nchild > frame_cap) {         // cannot happen (bound above); never write outside the stack
             if (lane == 0) atomicOr(acc.status, GSN_S_GRAPH_TOO_LARGE);
-            pos = frame_cap;
+            break;
         }
-        size = pos;
+        if (keep) { stack[2 * size] = kq0; stack[2 * size + 1] = wq1; }
+        if (child) {
+            const int at = size + nkeep + (nchild - 1 - __popc(mc & lt));
+            stack[2 * at] = cq0;
+            stack[2 * at + 1] = cq1;
+        }
+        size += nkeep + nchild;
         __syncwarp();
     }
 }
 
-template <int NT>
+// One instantiation per (search kind, scope): MODE 0 = cycles, 1 = induced cycles (warp-cooperative search), 2 = cliques /
+// generic patterns (per-thread search).  A CTA runs every phase once, with a cold instruction cache (clock64 stamps: the
+// 50-edge write-out took 16 k cycles in the all-in-one kernel of 127 KB of SASS, `stall_no_instruction` 3.2 per issue): a
+// launch should touch as little code as possible.
+template <int NT, int MODE, int SCOPE>
 __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__ CsParams prm) {
     extern __shared__ __align__(16) unsigned char cs_smem[];
     __shared__ int64_t sh_g[2], sh_e[2];
@@ -313,7 +354,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
     int32_t *colmap = rp + (prm.node_cap + 4);
     uint32_t *sacc = (uint32_t *)(colmap + prm.slot_cap);
     uint4 *stacks = (uint4 *)(sacc + prm.acc_words);
-    uint16_t *goff = (uint16_t *)(stacks + (size_t)(P.family == GSN_FAMILY_CYCLES ? NW * prm.frame_cap * 2 : 0));
+    uint16_t *goff = (uint16_t *)(stacks + (size_t)(MODE != 2 ? NW * prm.frame_cap * 2 : 0));
     if (nn > prm.node_cap) {          // cannot happen when every graph has <= 64 nodes (node_cap >= T + 64)
         if (tid == 0) atomicOr(prm.status, GSN_S_GRAPH_TOO_LARGE);
         return;
@@ -388,7 +429,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
         if (tid == 0) {
             int64_t g = pg;
             int n1 = pn0;
-            if (P.scope == 0) {
+            if (SCOPE == 0) {
                 g = g_hi;
                 n1 = nn;
             } else {
@@ -407,18 +448,18 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
         const int pn1 = sh_pass[0];
         const int64_t pg1 = pg + sh_pass[1];
         const int ps0 = rp[pn0], ps1 = rp[pn1];
-        const int rows = P.scope == 0 ? (pn1 - pn0) : (ps1 - ps0);
-        const bool in_smem = (int64_t)rows * C <= prm.acc_words && (P.scope == 0 || ps1 - ps0 <= prm.slot_cap);
-        if (P.scope == 1 && ps1 - ps0 > prm.slot_cap) {       // one graph denser than the edge_dict capacity: impossible
+        const int rows = SCOPE == 0 ? (pn1 - pn0) : (ps1 - ps0);
+        const bool in_smem = (int64_t)rows * C <= prm.acc_words && (SCOPE == 0 || ps1 - ps0 <= prm.slot_cap);
+        if (SCOPE == 1 && ps1 - ps0 > prm.slot_cap) {       // one graph denser than the edge_dict capacity: impossible
             if (tid == 0) atomicOr(prm.status, GSN_S_GRAPH_TOO_LARGE);     // (<= 64 * 63 slots <= slot_cap), kept as a guard
             return;
         }
         if (in_smem) {
             for (int i = tid; i < rows * C; i += NT) sacc[i] = 0u;
-        } else if (P.scope == 0) {
+        } else if (SCOPE == 0) {
             for (int i = tid; i < rows * C; i += NT) outc[(v0 + pn0 + i / C) * prm.out_ld + i % C] = 0;
         }
-        if (P.scope == 1) {
+        if (SCOPE == 1) {
             for (int i = tid; i < ps1 - ps0; i += NT) colmap[i] = -1;
             __syncthreads();
             // edge_dict (:142-144): the LAST edge_index column of a pair wins
@@ -439,14 +480,13 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
 
         CS_STAMP(3);      // pass set-up + edge_dict done
         CsAcc acc{in_smem ? sacc : nullptr, colmap, outc, prm.out_ld, v0, prm.status, C, ps0};
-        if (P.scope == 0) acc.sbase = 0;
+        if (SCOPE == 0) acc.sbase = 0;
         // vertex-scope rows are chunk-local nodes relative to the pass start
         CsAcc vacc = acc;
-        if (P.scope == 0 && in_smem) vacc.acc = sacc - (size_t)pn0 * C;
-        if (P.family == GSN_FAMILY_CYCLES) {
+        if (SCOPE == 0 && in_smem) vacc.acc = sacc - (size_t)pn0 * C;
+        if (MODE != 2) {
             uint4 *st = stacks + (size_t)warp * prm.frame_cap * 2;
-            if (P.induced) cycles_warp<true>(P, adj, rp, goff, pn0, pn1, &sh_ticket, st, prm.frame_cap, vacc, NW);
-            else cycles_warp<false>(P, adj, rp, goff, pn0, pn1, &sh_ticket, st, prm.frame_cap, vacc, NW);
+            cycles_warp<MODE == 1, SCOPE>(P, adj, rp, goff, pn0, pn1, &sh_ticket, st, prm.frame_cap, vacc, NW);
         } else {
             // per-thread DFS: one root vertex at a time through a shared ticket
             while (true) {
@@ -460,7 +500,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
                 while (nb) {
                     const int b = __ffsll((long long)nb) - 1;
                     nb &= nb - 1;
-                    if (P.family == GSN_FAMILY_CLIQUES) enumerate_cliques<1>(P.kmin, P.kmax, P.scope, Gv, a, b, ta);
+                    if (P.family == GSN_FAMILY_CLIQUES) enumerate_cliques<1>(P.kmin, P.kmax, SCOPE, Gv, a, b, ta);
                     else enumerate_generic<1>(P, Gv, a, b, ta);
                 }
             }
@@ -469,7 +509,7 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
         CS_STAMP(4);      // search done (all warps)
         // ---- write-out
         if (in_smem) {
-            if (P.scope == 0) {
+            if (SCOPE == 0) {
                 for (int i = tid; i < rows * C; i += NT) outc[(v0 + pn0 + i / C) * prm.out_ld + i % C] = (int64_t)sacc[i];
             } else {
                 for (int64_t e = e0 + tid; e < e1; e += NT) {
@@ -495,13 +535,27 @@ __global__ void __launch_bounds__(NT) count_small_kernel(const __grid_constant__
     }
 }
 
-template <int NT>
-static int cs_launch(const CsParams &prm, int64_t chunks, size_t smem, cudaStream_t stream) {
-    GSN_CUDA_OK(cudaFuncSetAttribute(count_small_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    count_small_kernel<NT><<<(unsigned)chunks, NT, smem, stream>>>(prm);
+template <int NT, int MODE, int SCOPE>
+static int cs_launch_one(const CsParams &prm, int64_t chunks, size_t smem, cudaStream_t stream) {
+    GSN_CUDA_OK(cudaFuncSetAttribute(count_small_kernel<NT, MODE, SCOPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    count_small_kernel<NT, MODE, SCOPE><<<(unsigned)chunks, NT, smem, stream>>>(prm);
     GSN_BUMP(1);
     GSN_LAUNCH_OK("count_small_kernel");
     return GSN_OK;
+}
+
+template <int NT>
+static int cs_launch(const CsParams &prm, int64_t chunks, size_t smem, cudaStream_t stream) {
+    const GsnPlan &P = prm.plan;
+    const int mode = P.family == GSN_FAMILY_CYCLES ? (P.induced ? 1 : 0) : 2;
+    if (P.scope == 0) {
+        if (mode == 0) return cs_launch_one<NT, 0, 0>(prm, chunks, smem, stream);
+        if (mode == 1) return cs_launch_one<NT, 1, 0>(prm, chunks, smem, stream);
+        return cs_launch_one<NT, 2, 0>(prm, chunks, smem, stream);
+    }
+    if (mode == 0) return cs_launch_one<NT, 0, 1>(prm, chunks, smem, stream);
+    if (mode == 1) return cs_launch_one<NT, 1, 1>(prm, chunks, smem, stream);
+    return cs_launch_one<NT, 2, 1>(prm, chunks, smem, stream);
 }
 
 }  // namespace gsn
