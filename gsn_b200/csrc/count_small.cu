@@ -607,7 +607,9 @@ extern "C" int gsn_count_small(const int64_t *d_edge_index, int64_t E, const int
         if (acc_words < 64 * C) acc_words = 64 * C;
     }
     prm.acc_words = (int32_t)((acc_words + 3) & ~3);
-    prm.frame_cap = P.family == GSN_FAMILY_CYCLES ? 32 * (P.kmax - 1) : 0;
+    // frames exist at depths 0 .. kmax - 3 and a level never holds more than 32 (see cycles_warp): the bound is tight, and
+    // shared memory is what limits the resident CTAs
+    prm.frame_cap = P.family == GSN_FAMILY_CYCLES ? 32 * (P.kmax > 3 ? P.kmax - 2 : 1) : 0;
     prm.out = d_out; prm.out_ld = out_ld; prm.status = d_status; prm.plan = P;
     const size_t smem = sizeof(uint64_t) * prm.node_cap + sizeof(int32_t) * (prm.node_cap + 4) + sizeof(int32_t) * prm.slot_cap +
                         sizeof(uint32_t) * prm.acc_words + (size_t)(NT / 32) * prm.frame_cap * 32 + sizeof(uint16_t) * prm.node_cap + 16;
