@@ -176,3 +176,25 @@ def test_flat_loader_batches_equal_collate_over_the_same_order():
         exp = collate([graphs[j] for j in order[3 * i:3 * i + 3]])
         for k in keys:
             assert torch.equal(getattr(exp, k), getattr(b, k)), (k, i)
+
+
+def test_tile_plan_capacity_bound():
+    """gsn_b200.fused_model.tile_plan sizes its buffer with min(G, 2N/128 + G/32 + 2); the greedy packing the kernel
+    performs (<= 128 rows, <= 32 graphs per tile, oversized graphs alone) never needs more, whatever the graph sizes"""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        G = int(rng.integers(1, 400))
+        kind = trial % 4
+        sizes = (rng.integers(0, 3, G) if kind == 0 else rng.integers(1, 129, G) if kind == 1
+                 else rng.integers(9, 38, G) if kind == 2 else rng.integers(0, 300, G))
+        N = int(sizes.sum())
+        tiles, g0 = 0, 0
+        while g0 < G:
+            g1, rows = g0, 0
+            while g1 < G and g1 - g0 < 32 and rows + sizes[g1] <= 128:
+                rows += sizes[g1]
+                g1 += 1
+            g0 = max(g1, g0 + 1)
+            tiles += 1
+        assert tiles <= min(G, 2 * N // 128 + G // 32 + 2), (trial, G, N, tiles)
