@@ -162,6 +162,28 @@ def bytes_per_step(N, E, G):
 # ======================================================================================
 # our arm
 # ======================================================================================
+def other_configs(local_rank):
+    """BASELINE configs 3 / 4 / 5 through their own scripts (scripts/bench_ogb.py, bench_imdb.py, bench_count.py) as child
+    processes on the same GPU; each prints one JSON line.  A failure or a time-out is recorded, never raised."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get('CUDA_VISIBLE_DEVICES', str(local_rank)))
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    jobs = {'config3_molhiv_train_step_b512': ['scripts/bench_ogb.py', '--steps', '10', '--warmup', '3'],
+            'config4_imdb_cliques_k5': ['scripts/bench_imdb.py', '--reps', '10'],
+            'config5_count_cycles_k12_131072_graphs': ['scripts/bench_count.py', '--graphs', '131072', '--k', '12', '--check', '100']}
+    out = {}
+    for name, cmd in jobs.items():
+        try:
+            r = subprocess.run([sys.executable] + cmd, cwd=here, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                               text=True, timeout=240)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+            out[name] = json.loads(lines[-1]) if lines else {'error': f'no JSON line (exit {r.returncode})'}
+        except Exception as ex:
+            out[name] = {'error': repr(ex)[:200]}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     from gsn_b200 import _lib, counting, patterns
     from gsn_b200.network import GNNSubstructures
@@ -415,6 +437,12 @@ def run_ours(args, rank, world, local_rank):
                 gsn_v = gsn_v_line(dev, raw[:64], flush, S)
             except Exception as ex:
                 gsn_v = {'error': repr(ex)[:200]}
+        # ---- the other BASELINE configs on this GPU (their own scripts, one JSON line each; informative, never fatal):
+        # 3 = molhiv-recipe training step, 4 = IMDB-BINARY fixture (cliques k <= 5), 5 = counting throughput (cycles k <= 12,
+        # a 131,072-graph sample of the 1 M-graph workload)
+        other = None
+        if not args.no_sweep and world == 1:
+            other = other_configs(local_rank)
         # reported baselines: rank 0 at N=1 only (the multi-GPU runs of the scaling sweep stay short)
         cpu = cpu_baseline(raw[0], sds_oracle(), encoder, model, budget_s=12.0) if world == 1 else None
         eager = None
@@ -455,6 +483,7 @@ def run_ours(args, rank, world, local_rank):
                                          'note': 'host time to enqueue a step (BucketedPipeline.submit = one native call: packed copy + graph launch [+ read-back]) in the two timed regions'},
             'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'kernels_us': kernels_us, 'sweep': sweep,
             'scatter_kernels': scatter_kernels, 'roofline_large_batch': roof_large, 'torch_eager_gpu': eager, 'gsn_v': gsn_v,
+            'other_configs': other,
         }
     return line
 
